@@ -1,0 +1,279 @@
+/* g4hepem_b200.h -- C-ABI of the B200-native G4HepEm stepping path.
+ *
+ * This is the drop-in boundary: a host program (the G4HepEm C++ managers, a tracking
+ * manager, a Python harness over ctypes) calls these entry points with plain pointers and
+ * sizes.  Each entry point names the reference interface it replaces (paths relative to
+ * G4HepEm/ in mnovak42/g4hepem).
+ *
+ * Units follow Geant4 internal units (MeV, mm).  All functions return 0 on success, a
+ * negative G4HB200_E* code otherwise; they never call exit() (the reference's gpuErrchk does,
+ * G4HepEmData/include/G4HepEmCuUtils.hh:19-26).
+ *
+ * There is no CPU fallback: every compute entry point launches sm_100a kernels and fails with
+ * G4HB200_ENODEVICE when no CUDA device is usable.
+ */
+#ifndef G4HEPEM_B200_H
+#define G4HEPEM_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define G4HB200_OK 0
+#define G4HB200_EINVAL (-1)    /* bad argument / inconsistent table sizes */
+#define G4HB200_ENODEVICE (-2) /* no usable CUDA device */
+#define G4HB200_ECUDA (-3)     /* CUDA runtime error (see g4hb200_last_error) */
+#define G4HB200_ENOMEM (-4)
+#define G4HB200_ECAPACITY (-5) /* batch / secondary queue capacity exceeded */
+
+/* ------------------------------------------------------------------------------------------
+ * Flat table descriptor: the content of G4HepEmData + G4HepEmParameters as plain arrays.
+ * Replaces CopyG4HepEmDataToGPU / CopyG4HepEmParametersToGPU (G4HepEmData/src/G4HepEmData.cc:78-101,
+ * G4HepEmData/src/G4HepEmParameters.cc) -- the AoS-of-pointers deep copy becomes one contiguous
+ * device arena.  Array layouts are the reference's (G4HepEmData/include/G4HepEm*Data.hh).
+ * ------------------------------------------------------------------------------------------ */
+typedef struct G4HB200ElectronTables { /* G4HepEmElectronData (G4HepEmElectronData.hh:81-354) */
+  int32_t num_loss;                    /* fELossEnergyGridSize */
+  double loss_log_min_ekin;            /* fELossLogMinEkin */
+  double loss_eil_delta;               /* fELossEILDelta */
+  const double* loss_egrid;            /* [num_loss] */
+  const double* loss_data;             /* [5*num_loss*num_matcut] range,sd | dedx,sd | inv-range sd */
+  const int32_t* resmx_start;          /* [num_matcut] fResMacXSecStartIndexPerMatCut */
+  const double* resmx_data;            /* [num_resmx] fResMacXSecData */
+  int32_t num_resmx;
+  double enuc_log_min_ekin;            /* fENucLogMinEkin */
+  double enuc_eil_delta;               /* fENucEILDelta */
+  const double* enuc_egrid;            /* [128] */
+  const double* enuc_data;             /* [2*128*num_mat] */
+  const double* tr1_data;              /* [2*num_loss*num_mat] */
+  const int32_t* sel_ioni_start;       /* [num_matcut] (-1: single element) */
+  const double* sel_ioni_data;
+  int32_t num_sel_ioni;
+  const int32_t* sel_sb_start;
+  const double* sel_sb_data;
+  int32_t num_sel_sb;
+  const int32_t* sel_rb_start;
+  const double* sel_rb_data;
+  int32_t num_sel_rb;
+} G4HB200ElectronTables;
+
+typedef struct G4HB200Tables {
+  /* G4HepEmParameters (G4HepEmParameters.hh:51-92) */
+  double electron_tracking_cut;
+  double gamma_tracking_cut;
+  double min_loss_table_energy;
+  double electron_brem_model_lim;
+  int32_t is_msc_positron_cor;
+  int32_t is_msc_displacement;
+  int32_t num_regions;
+  /* per region, G4HepEmRegionParmeters (G4HepEmParameters.hh:24-48): 8 doubles each:
+   * final_range, dr_over_range, lin_eloss_limit, msc_range_factor, msc_safety_factor,
+   * is_msc_minimal_step_limit, is_eloss_fluctuation, is_multiple_steps_in_msc_trans (flags as 0/1) */
+  const double* region_pars;
+  /* G4HepEmMatCutData (G4HepEmMatCutData.hh:41-68) */
+  int32_t num_matcut;
+  const double* mc_cuts;  /* [4*num_matcut] el cut, pos cut, gamma cut, log gamma cut */
+  const int32_t* mc_imat; /* [num_matcut] fHepEmMatIndex */
+  const int32_t* mc_ireg; /* [num_matcut] fG4RegionIndex */
+  /* G4HepEmMaterialData (G4HepEmMaterialData.hh:41-90) */
+  int32_t num_mat;
+  const int32_t* mat_num_elem;   /* [num_mat] */
+  const int32_t* mat_elem_start; /* [num_mat] offset into mat_elem_z / mat_elem_natoms */
+  const int32_t* mat_elem_z;     /* [sum num_elem] */
+  const double* mat_elem_natoms; /* [sum num_elem] fNumOfAtomsPerVolumeVect */
+  /* [16*num_mat]: density_cor_factor, electron_density, radiation_length, mean_exc_energy, zeff,
+   * zeff23, zeff_sqrt, umsc_par, umsc_stepmin[2], umsc_tail[4], umsc_theta[2] */
+  const double* mat_pars;
+  const int32_t* mat_sandia_num;   /* [num_mat] */
+  const int32_t* mat_sandia_start; /* [num_mat] offset into sandia_energies (x4 into sandia_cof) */
+  /* G4HepEmElementData (G4HepEmElementData.hh:36-85), indexed by Z in [0,120] */
+  /* [12*121]: zet, zet13, zet23, coulomb, logz, zfactor1, delta_max_low, delta_max_high, il_var_s1,
+   * il_var_s1_cond, kshell_binding, unused */
+  const double* elem_pars;
+  const int32_t* elem_sandia_num;   /* [121] */
+  const int32_t* elem_sandia_start; /* [121] */
+  int32_t num_sandia;               /* total Sandia intervals (materials + elements) */
+  const double* sandia_energies;    /* [num_sandia] */
+  const double* sandia_cof;         /* [4*num_sandia] */
+  /* e- / e+ */
+  G4HB200ElectronTables electron;
+  G4HB200ElectronTables positron;
+  /* G4HepEmSBTableData (G4HepEmSBTableData.hh:8-42) */
+  double sb_log_min_el_energy;
+  double sb_il_delta_el_energy;
+  const double* sb_el_energy;       /* [65] */
+  const double* sb_lel_energy;      /* [65] */
+  const double* sb_lkappa;          /* [54] */
+  const int32_t* sb_gcut_start;     /* [num_matcut] fGammaCutIndxStartIndexPerMC */
+  const int32_t* sb_gcut_indices;   /* [num_sb_gcut] fGammaCutIndices */
+  int32_t num_sb_gcut;
+  const int32_t* sb_start_per_z;    /* [121] */
+  const double* sb_data;            /* [num_sb_data] */
+  int32_t num_sb_data;
+  /* G4HepEmGammaData (G4HepEmGammaData.hh:15-79) */
+  int32_t gm_data_per_mat, gm_num_data0, gm_num_data1;
+  double gm_emax0, gm_log_emin0, gm_eil_delta0;
+  double gm_emax1, gm_log_emin1, gm_eil_delta1;
+  double gm_log_emin2, gm_eil_delta2;
+  const double* gm_mxsec;           /* [num_mat*gm_data_per_mat] */
+  int32_t gm_conv_egrid_size;
+  double gm_conv_log_min_ekin, gm_conv_eil_delta;
+  const int32_t* gm_conv_start;     /* [num_mat] */
+  const double* gm_conv_egrid;      /* [gm_conv_egrid_size] */
+  const double* gm_conv_data;
+  int32_t num_gm_conv;
+} G4HB200Tables;
+
+/* ------------------------------------------------------------------------------------------
+ * Track batches: structure of (paired) arrays.  Every double group is an array of n
+ * {a,b} pairs (16 B per track, one 128-bit load per thread, a warp reads 512 contiguous bytes).
+ * The same struct describes a host staging batch (pointers into pinned host memory) and a
+ * device batch; which one is meant is stated per entry point.  A NULL group is not touched.
+ *
+ * flags bits (G4HepEmTrack/G4HepEmMSCTrackData booleans): */
+#define G4HB200_F_POSITRON 0x01u        /* charge > 0 (G4HepEmTrack::fCharge) */
+#define G4HB200_F_ON_BOUNDARY 0x02u     /* G4HepEmTrack::fOnBoundary */
+#define G4HB200_F_MSC_FIRST_STEP 0x04u  /* G4HepEmMSCTrackData::fIsFirstStep */
+#define G4HB200_F_MSC_ACTIVE 0x08u      /* fIsActive */
+#define G4HB200_F_MSC_DISPLACE 0x10u    /* fIsDisplace */
+#define G4HB200_F_MSC_NO_SCATTER 0x20u  /* fIsNoScatteringInMSC */
+#define G4HB200_F_GAUSS_CACHED 0x40u    /* G4HepEmRandomEngine::fIsGauss */
+
+/* e-/e+ state: G4HepEmElectronTrack (G4HepEmRun/include/G4HepEmElectronTrack.hh:20-93) */
+typedef struct G4HB200ElectronBatch {
+  int64_t n;
+  /* persistent between steps (read+written every step) */
+  double* ekin_logekin;    /* {fEKin, fLogEKin (>99: not cached, G4HepEmTrack.hh:95-100)} */
+  double* dirx_diry;       /* fDirection[0,1] */
+  double* dirz_safety;     /* fDirection[2], fSafety */
+  double* nia01;           /* fNumIALeft[0,1] (ioni, brem) */
+  double* nia23;           /* fNumIALeft[2,3] (annihilation, lepto-nuclear) */
+  double* msc_irange_dynrf;/* fInitialRange, fDynamicRangeFactor */
+  double* msc_tlimmin_gauss;/* fTlimitMin, cached Gaussian variate (G4HepEmRandomEngine::fGauss) */
+  int32_t* meta;           /* int4 per track: {fMCIndex, flags, fID, rng draw counter} */
+  /* step results */
+  double* gstep_pstep;     /* fGStepLength, fPStepLength */
+  double* edep_dispx;      /* fEDeposit, MSC fDisplacement[0] */
+  double* dispy_dispz;     /* MSC fDisplacement[1,2] */
+  int32_t* winner;         /* fPIndxWon */
+  /* HowFar -> Perform hand-over (only used when the two run as separate launches) */
+  double* mfp01;           /* fMFPs[0,1] */
+  double* mfp23;           /* fMFPs[2,3] */
+  double* range_lambtr1;   /* fRange, MSC fLambtr1 */
+  double* tstep_zpath;     /* MSC fTrueStepLength, fZPathLength */
+  double* par12;           /* MSC fPar1, fPar2 */
+  double* par3_pad;        /* MSC fPar3, unused */
+} G4HB200ElectronBatch;
+
+/* gamma state: G4HepEmGammaTrack (G4HepEmRun/include/G4HepEmGammaTrack.hh:17-46) */
+typedef struct G4HB200GammaBatch {
+  int64_t n;
+  double* ekin_logekin; /* {fEKin, fLogEKin} */
+  double* dirx_diry;
+  double* dirz_nia0;    /* fDirection[2], fNumIALeft[0] */
+  int32_t* meta;        /* int4: {fMCIndex, flags, fID, rng draw counter} */
+  double* gstep_mfp0;   /* fGStepLength, fMFPs[0] */
+  double* edep_pemxsec; /* fEDeposit, fPEmxSec */
+  int32_t* winner;      /* fPIndxWon */
+} G4HB200GammaBatch;
+
+/* secondaries: what G4HepEmTLData::AddSecondary{Electron,Gamma}Track hands back
+ * (G4HepEmRun/include/G4HepEmTLData.hh:52-82), as an append-only queue. */
+#define G4HB200_SEC_ELECTRON 0
+#define G4HB200_SEC_POSITRON 1
+#define G4HB200_SEC_GAMMA 2
+typedef struct G4HB200SecondaryQueue {
+  int64_t capacity;
+  double* dirx_diry;  /* [capacity] pairs */
+  double* dirz_ekin;  /* [capacity] pairs */
+  int32_t* parent_kind; /* int2: {parent fID, G4HB200_SEC_*}; slot order within a parent is preserved */
+  int32_t* parent_slot; /* int2: {index of the parent track in its batch, 0/1 = first/second secondary} */
+  int32_t* count;     /* [1] number of valid entries */
+} G4HB200SecondaryQueue;
+
+typedef struct G4HB200 G4HB200; /* opaque handle: device arena with the flattened tables */
+
+/* ---- life cycle ------------------------------------------------------------------------- */
+/* Flatten + upload the tables to `device`.  Replaces InitG4HepEmData/CopyG4HepEmDataToGPU. */
+int g4hb200_create(const G4HB200Tables* tables, int device, G4HB200** out);
+int g4hb200_destroy(G4HB200* h);
+const char* g4hb200_last_error(void);
+int g4hb200_device_count(void);
+
+/* Device batch management (library-owned device memory). */
+int g4hb200_electron_batch_alloc(G4HB200* h, int64_t capacity, G4HB200ElectronBatch* out_dev);
+int g4hb200_electron_batch_free(G4HB200* h, G4HB200ElectronBatch* dev);
+int g4hb200_gamma_batch_alloc(G4HB200* h, int64_t capacity, G4HB200GammaBatch* out_dev);
+int g4hb200_gamma_batch_free(G4HB200* h, G4HB200GammaBatch* dev);
+int g4hb200_secondary_queue_alloc(G4HB200* h, int64_t capacity, G4HB200SecondaryQueue* out_dev);
+int g4hb200_secondary_queue_free(G4HB200* h, G4HB200SecondaryQueue* dev);
+int g4hb200_secondary_queue_reset(G4HB200* h, G4HB200SecondaryQueue* dev, void* stream);
+/* host <-> device copies of the non-NULL groups (n tracks), asynchronous on `stream` */
+int g4hb200_electron_batch_upload(G4HB200* h, const G4HB200ElectronBatch* host, G4HB200ElectronBatch* dev, void* stream);
+int g4hb200_electron_batch_download(G4HB200* h, const G4HB200ElectronBatch* dev, G4HB200ElectronBatch* host, void* stream);
+int g4hb200_gamma_batch_upload(G4HB200* h, const G4HB200GammaBatch* host, G4HB200GammaBatch* dev, void* stream);
+int g4hb200_gamma_batch_download(G4HB200* h, const G4HB200GammaBatch* dev, G4HB200GammaBatch* host, void* stream);
+int g4hb200_secondary_queue_download(G4HB200* h, const G4HB200SecondaryQueue* dev, G4HB200SecondaryQueue* host, void* stream);
+int g4hb200_sync(G4HB200* h, void* stream);
+
+/* ---- table look-ups (BASELINE config 1) ---------------------------------------------------
+ * One launch evaluates, per track, G4HepEmElectronManager::GetRestRange, GetRestDEDX,
+ * GetInvRange(range), GetRestMacXSec(ioni), GetRestMacXSec(brem), GetMacXSecNuclear,
+ * GetTransportMFP (G4HepEmElectronManager.icc:486-582).  All pointers are device pointers;
+ * out is 7 arrays of n doubles: out[k*n + i]. is_electron selects e- / e+ tables. */
+int g4hb200_electron_lookups(G4HB200* h, int64_t n, const int32_t* imc, const double* ekin, const double* logekin,
+                             int is_electron, double* out, void* stream);
+/* G4HepEmElectronManager::GetRestMacXSecForStepping (ioni, brem), GetMacXSecNuclearForStepping,
+ * ComputeMacXsecAnnihilationForStepping (.icc:544-599): out[k*n+i], k = 0..3 */
+int g4hb200_electron_stepping_xsecs(G4HB200* h, int64_t n, const int32_t* imc, const double* ekin, const double* logekin,
+                                    int is_electron, double* out, void* stream);
+/* G4HepEmGammaManager::GetTotalMacXSec + SampleInteraction with a caller supplied uniform
+ * (G4HepEmGammaManager.icc:108-152,173-219): out_mxsec[n], out_pid[n] */
+int g4hb200_gamma_lookups(G4HB200* h, int64_t n, const int32_t* imc, const double* ekin, const double* logekin,
+                          const double* urnd, double* out_mxsec, int32_t* out_pid, void* stream);
+/* Target element selectors with a caller supplied uniform: kind 0 = brem SB, 1 = brem RB
+ * (G4HepEmElectronInteractionBrem.icc:266-296), 2 = conversion (G4HepEmGammaInteractionConversion.icc:151-176;
+ * imc is then the material index).  out_elem[n]. */
+int g4hb200_select_target_element(G4HB200* h, int kind, int is_electron, int64_t n, const int32_t* imc,
+                                  const double* ekin, const double* logekin, const double* urnd,
+                                  int32_t* out_elem, void* stream);
+/* device VDT log / exp (G4HepEmLog.hh:228-263, G4HepEmExp.hh:182-223), for bit-exactness tests */
+int g4hb200_vdt_log_exp(G4HB200* h, int64_t n, const double* x, double* out_log, double* out_exp, void* stream);
+/* the counter based uniform stream: out[i*ndraw + j] = draw j of track id[i] */
+int g4hb200_rng_uniforms(G4HB200* h, uint64_t seed, int64_t n, const int32_t* track_id, int32_t ndraw,
+                         double* out, void* stream);
+
+/* ---- stepping entry points (device batches) ------------------------------------------------
+ * seed: global seed of the counter based stream; the per-track key is (seed, fID) and the
+ * draw counter lives in meta[3], so results do not depend on batch order or launch shape. */
+/* G4HepEmElectronManager::HowFar(data, pars, tlData) (.icc:35-45): resample fNumIALeft,
+ * HowFarToDiscreteInteraction (.icc:48-101) and HowFarToMSC (.icc:103-164). */
+int g4hb200_electron_howfar(G4HB200* h, G4HB200ElectronBatch* dev, uint64_t seed, void* stream);
+/* G4HepEmElectronManager::Perform(data, pars, tlData) (.icc:461-483): continuous part, then e+
+ * annihilation at rest or the discrete interaction; secondaries are appended to `sec`. */
+int g4hb200_electron_perform(G4HB200* h, G4HB200ElectronBatch* dev, G4HB200SecondaryQueue* sec, uint64_t seed, void* stream);
+/* HowFar + (geometry accepts the proposed step, fOnBoundary unchanged) + Perform in one pass:
+ * the hand-over groups stay in registers. */
+int g4hb200_electron_step(G4HB200* h, G4HB200ElectronBatch* dev, G4HB200SecondaryQueue* sec, uint64_t seed, void* stream);
+/* G4HepEmGammaManager::HowFar (.icc:27-48) */
+int g4hb200_gamma_howfar(G4HB200* h, G4HB200GammaBatch* dev, uint64_t seed, void* stream);
+/* G4HepEmGammaManager::SelectInteraction (.icc:173-219; skipped when on boundary, as the
+ * callers do: G4HepEmTrackingManager.cc:1092-1108) followed by Perform (.icc:54-94). */
+int g4hb200_gamma_perform(G4HB200* h, G4HB200GammaBatch* dev, G4HB200SecondaryQueue* sec, uint64_t seed, void* stream);
+int g4hb200_gamma_step(G4HB200* h, G4HB200GammaBatch* dev, G4HB200SecondaryQueue* sec, uint64_t seed, void* stream);
+
+/* ---- host-buffer entry points (the call a host application makes) ---------------------------
+ * Upload the persistent groups of `host`, run the fused step, download state + results and the
+ * secondaries; everything asynchronous on the handle's internal stream, then synchronised. */
+int g4hb200_electron_step_host(G4HB200* h, G4HB200ElectronBatch* host, G4HB200SecondaryQueue* host_sec, uint64_t seed);
+int g4hb200_gamma_step_host(G4HB200* h, G4HB200GammaBatch* host, G4HB200SecondaryQueue* host_sec, uint64_t seed);
+
+/* number of kernels launched through this handle so far (for the bench's gpu_launches) */
+int64_t g4hb200_launch_count(const G4HB200* h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* G4HEPEM_B200_H */

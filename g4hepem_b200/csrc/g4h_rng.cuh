@@ -1,0 +1,132 @@
+// g4h_rng.cuh -- per-track counter based uniform stream + the reference's Gauss / Poisson on top.
+//
+// Stream definition (must match oracle/g4h_rng_host.h, the stream injected into the CPU
+// reference through G4HepEmRandomEngine::flat/flatArray):
+//   u(seed, id, j) = (2k+1) * 2^-53,  k = top 52 bits of word pair (j&1) of
+//   Philox4x32-10(counter = {j>>1, 0, id, 0}, key = {seed lo, seed hi})
+// A Philox block yields two uniforms; the second one is kept in registers so consecutive draws
+// cost one block per pair.  Gauss()/Poisson() restate G4HepEmRandomEngine.hh:50-97, including
+// the cached second Box-Muller variate, which is per-track state here (the reference keeps it in
+// the per-worker engine).
+#ifndef G4H_RNG_CUH
+#define G4H_RNG_CUH
+
+#include "g4h_math.cuh"
+
+namespace g4h {
+
+G4H_FN uint32_t MulHi32(uint32_t a, uint32_t b) {
+#if defined(__CUDA_ARCH__)
+  return __umulhi(a, b);
+#else
+  return static_cast<uint32_t>((static_cast<uint64_t>(a) * b) >> 32);
+#endif
+}
+
+struct Rng {
+  uint32_t k0, k1;     // key: global seed
+  uint32_t id;         // track id
+  uint32_t draw;       // index of the next uniform
+  uint32_t cachedBlk;  // block index whose second pair is cached (0xffffffff: none)
+  uint32_t c2, c3;     // cached words
+  bool hasGauss;       // G4HepEmRandomEngine::fIsGauss
+  double gauss;        // G4HepEmRandomEngine::fGauss
+
+  G4H_MFN void Init(uint64_t seed, uint32_t trackId, uint32_t firstDraw, bool isGauss, double gaussVal) {
+    k0 = static_cast<uint32_t>(seed);
+    k1 = static_cast<uint32_t>(seed >> 32);
+    id = trackId;
+    draw = firstDraw;
+    cachedBlk = 0xffffffffu;
+    c2 = c3 = 0u;
+    hasGauss = isGauss;
+    gauss = gaussVal;
+  }
+
+  G4H_MFN static double ToUniform(uint32_t lo, uint32_t hi) {
+    // (2k+1) * 2^-53 with k the top 52 bits of hi:lo -- exact: build 1.m in [1,2) and subtract (1 - 2^-53)
+    const uint64_t bits = (static_cast<uint64_t>(hi) << 32) | lo;
+    const double d = FromBits(0x3FF0000000000000ULL | (bits >> 12));
+    return d - 0.99999999999999988897769753748;  // 1 - 2^-53
+  }
+
+  G4H_MFN void Block(uint32_t blk, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) const {
+    uint32_t x0 = blk, x1 = 0u, x2 = id, x3 = 0u;
+    uint32_t ka = k0, kb = k1;
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+      const uint32_t hi0 = MulHi32(0xD2511F53u, x0);
+      const uint32_t lo0 = 0xD2511F53u * x0;
+      const uint32_t hi1 = MulHi32(0xCD9E8D57u, x2);
+      const uint32_t lo1 = 0xCD9E8D57u * x2;
+      const uint32_t n0 = hi1 ^ x1 ^ ka;
+      const uint32_t n2 = hi0 ^ x3 ^ kb;
+      x0 = n0; x1 = lo1; x2 = n2; x3 = lo0;
+      ka += 0x9E3779B9u;
+      kb += 0xBB67AE85u;
+    }
+    r0 = x0; r1 = x1; r2 = x2; r3 = x3;
+  }
+
+  // G4HepEmRandomEngine::flat()
+  G4H_MFN double Flat() {
+    const uint32_t j = draw++;
+    const uint32_t blk = j >> 1;
+    if (j & 1u) {
+      if (blk == cachedBlk) return ToUniform(c2, c3);
+      uint32_t r0, r1, r2, r3;
+      Block(blk, r0, r1, r2, r3);
+      return ToUniform(r2, r3);
+    }
+    uint32_t r0, r1;
+    Block(blk, r0, r1, c2, c3);
+    cachedBlk = blk;
+    return ToUniform(r0, r1);
+  }
+
+  // G4HepEmRandomEngine::Gauss (G4HepEmRandomEngine.hh:50-67): polar Box-Muller, second variate cached
+  G4H_MFN double Gauss(double mean, double stDev) {
+    if (hasGauss) {
+      hasGauss = false;
+      return gauss * stDev + mean;
+    }
+    double r, v1, v2;
+    do {
+      const double u0 = Flat();
+      const double u1 = Flat();
+      v1 = 2. * u0 - 1.;
+      v2 = 2. * u1 - 1.;
+      r = v1 * v1 + v2 * v2;
+    } while (r > 1.);
+    const double fac = sqrt(-2. * Log(r) / r);
+    gauss = v1 * fac;
+    hasGauss = true;
+    return v2 * fac * stDev + mean;
+  }
+
+  // G4HepEmRandomEngine::Poisson (G4HepEmRandomEngine.hh:74-97)
+  G4H_MFN int Poisson(double mean) {
+    const int border = 16;
+    const double limit = 2.E+9;
+    int number = 0;
+    if (mean <= border) {
+      const double position = Flat();
+      double poissonValue = Exp(-mean);
+      double poissonSum = poissonValue;
+      while (poissonSum <= position) {
+        ++number;
+        poissonValue *= mean / number;
+        poissonSum += poissonValue;
+      }
+      return number;
+    }
+    const double u0 = Flat();
+    const double u1 = Flat();
+    const double t = sqrt(-2. * Log(u0)) * cos(k2Pi * u1);
+    const double value = mean + t * sqrt(mean) + 0.5;
+    return value < 0. ? 0 : value >= limit ? static_cast<int>(limit) : static_cast<int>(value);
+  }
+};
+
+}  // namespace g4h
+#endif

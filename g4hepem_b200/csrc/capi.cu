@@ -1,0 +1,641 @@
+// capi.cu -- implementation of the C-ABI (include/g4hepem_b200.h): table arena, batch memory and
+// kernel launches.  Built for sm_100a only (see __graft_entry__.build()).  No CPU fallback: every
+// compute entry point launches a kernel or returns an error.
+#include <cuda_runtime.h>
+
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "../../include/g4hepem_b200.h"
+#include "g4h_kernels.cuh"
+#include "g4h_view.cuh"
+
+using namespace g4h;
+
+namespace {
+
+thread_local std::string g_lastError;
+
+int Fail(int code, const char* what, cudaError_t err = cudaSuccess) {
+  g_lastError = what;
+  if (err != cudaSuccess) {
+    g_lastError += ": ";
+    g_lastError += cudaGetErrorString(err);
+  }
+  return code;
+}
+
+#define G4H_CUDA(call)                                              \
+  do {                                                              \
+    const cudaError_t err__ = (call);                               \
+    if (err__ != cudaSuccess) return Fail(G4HB200_ECUDA, #call, err__); \
+  } while (0)
+
+// collects host arrays, packs them into one arena (doubles, then int32s, 16-byte aligned pieces)
+struct ArenaBuilder {
+  struct Piece {
+    const void* src;
+    size_t bytes;
+    size_t offset;
+    const void** dst;  // where the device pointer goes
+  };
+  std::vector<Piece> pieces;
+  size_t total = 0;
+  template <class T>
+  void Add(const T*& field, size_t count) {
+    const T* src = field;
+    if (src == nullptr || count == 0) {
+      field = nullptr;
+      return;
+    }
+    const size_t bytes = count * sizeof(T);
+    pieces.push_back(Piece{src, bytes, total, reinterpret_cast<const void**>(&field)});
+    total += (bytes + 255) & ~static_cast<size_t>(255);
+  }
+};
+
+void AddElectron(ArenaBuilder& ab, G4HB200ElectronTables& e, int numMatCut, int numMat) {
+  ab.Add(e.loss_egrid, e.num_loss);
+  ab.Add(e.loss_data, static_cast<size_t>(5) * e.num_loss * numMatCut);
+  ab.Add(e.resmx_start, numMatCut);
+  ab.Add(e.resmx_data, e.num_resmx);
+  ab.Add(e.enuc_egrid, 128);
+  ab.Add(e.enuc_data, static_cast<size_t>(2) * 128 * numMat);
+  ab.Add(e.tr1_data, static_cast<size_t>(2) * e.num_loss * numMat);
+  ab.Add(e.sel_ioni_start, numMatCut);
+  ab.Add(e.sel_ioni_data, e.num_sel_ioni);
+  ab.Add(e.sel_sb_start, numMatCut);
+  ab.Add(e.sel_sb_data, e.num_sel_sb);
+  ab.Add(e.sel_rb_start, numMatCut);
+  ab.Add(e.sel_rb_data, e.num_sel_rb);
+}
+
+int GridFor(int64_t n, int smCount, int ctasPerSM) {
+  const int64_t want = (n + kThreadsPerBlock - 1) / kThreadsPerBlock;
+  const int64_t full = static_cast<int64_t>(smCount) * ctasPerSM;
+  if (want <= 0) return 1;
+  if (want >= full) return static_cast<int>(full);
+  // round up to a multiple of the SM count so that every SM gets the same number of CTAs
+  const int64_t rounded = ((want + smCount - 1) / smCount) * smCount;
+  return static_cast<int>(rounded < full ? rounded : full);
+}
+
+}  // namespace
+
+struct G4HB200 {
+  int device = 0;
+  int smCount = 148;
+  void* arena = nullptr;
+  size_t arenaBytes = 0;
+  G4HB200Tables desc;  // descriptor with device pointers
+  TablesView view;
+  cudaStream_t stream = nullptr;  // internal stream of the *_host entry points
+  int64_t launches = 0;
+  // device scratch of the *_host entry points
+  G4HB200ElectronBatch elDev;
+  G4HB200GammaBatch gmDev;
+  G4HB200SecondaryQueue secDev;
+  int64_t elCap = 0, gmCap = 0, secCap = 0;
+};
+
+namespace {
+
+template <class T>
+int DevAlloc(T*& p, size_t count) {
+  void* q = nullptr;
+  const cudaError_t err = cudaMalloc(&q, count * sizeof(T) > 0 ? count * sizeof(T) : 16);
+  if (err != cudaSuccess) return Fail(err == cudaErrorMemoryAllocation ? G4HB200_ENOMEM : G4HB200_ECUDA, "cudaMalloc", err);
+  p = static_cast<T*>(q);
+  return 0;
+}
+
+void ElectronDoubleGroups(G4HB200ElectronBatch* b, double** out[16]) {
+  double** g[16] = {&b->ekin_logekin, &b->dirx_diry, &b->dirz_safety, &b->nia01, &b->nia23, &b->msc_irange_dynrf,
+                    &b->msc_tlimmin_gauss, &b->gstep_pstep, &b->edep_dispx, &b->dispy_dispz, &b->mfp01, &b->mfp23,
+                    &b->range_lambtr1, &b->tstep_zpath, &b->par12, &b->par3_pad};
+  for (int i = 0; i < 16; ++i) out[i] = g[i];
+}
+
+void GammaDoubleGroups(G4HB200GammaBatch* b, double** out[5]) {
+  double** g[5] = {&b->ekin_logekin, &b->dirx_diry, &b->dirz_nia0, &b->gstep_mfp0, &b->edep_pemxsec};
+  for (int i = 0; i < 5; ++i) out[i] = g[i];
+}
+
+int CopyGroup(void* dst, const void* src, size_t bytes, cudaMemcpyKind kind, cudaStream_t st) {
+  if (dst == nullptr || src == nullptr || bytes == 0) return 0;
+  G4H_CUDA(cudaMemcpyAsync(dst, src, bytes, kind, st));
+  return 0;
+}
+
+int CopyElectron(const G4HB200ElectronBatch* from, G4HB200ElectronBatch* to, cudaMemcpyKind kind, cudaStream_t st,
+                 int firstGroup, int lastGroup, bool withMeta, bool withWinner) {
+  const int64_t n = from->n;
+  double** gf[16];
+  double** gt[16];
+  ElectronDoubleGroups(const_cast<G4HB200ElectronBatch*>(from), gf);
+  ElectronDoubleGroups(to, gt);
+  for (int i = firstGroup; i < lastGroup; ++i) {
+    const int rc = CopyGroup(*gt[i], *gf[i], static_cast<size_t>(n) * 16, kind, st);
+    if (rc != 0) return rc;
+  }
+  if (withMeta) {
+    const int rc = CopyGroup(to->meta, from->meta, static_cast<size_t>(n) * 16, kind, st);
+    if (rc != 0) return rc;
+  }
+  if (withWinner) {
+    const int rc = CopyGroup(to->winner, from->winner, static_cast<size_t>(n) * 4, kind, st);
+    if (rc != 0) return rc;
+  }
+  to->n = n;
+  return 0;
+}
+
+int CopyGamma(const G4HB200GammaBatch* from, G4HB200GammaBatch* to, cudaMemcpyKind kind, cudaStream_t st, int firstGroup,
+              int lastGroup, bool withMeta, bool withWinner) {
+  const int64_t n = from->n;
+  double** gf[5];
+  double** gt[5];
+  GammaDoubleGroups(const_cast<G4HB200GammaBatch*>(from), gf);
+  GammaDoubleGroups(to, gt);
+  for (int i = firstGroup; i < lastGroup; ++i) {
+    const int rc = CopyGroup(*gt[i], *gf[i], static_cast<size_t>(n) * 16, kind, st);
+    if (rc != 0) return rc;
+  }
+  if (withMeta) {
+    const int rc = CopyGroup(to->meta, from->meta, static_cast<size_t>(n) * 16, kind, st);
+    if (rc != 0) return rc;
+  }
+  if (withWinner) {
+    const int rc = CopyGroup(to->winner, from->winner, static_cast<size_t>(n) * 4, kind, st);
+    if (rc != 0) return rc;
+  }
+  to->n = n;
+  return 0;
+}
+
+int CheckHandle(G4HB200* h) {
+  if (h == nullptr) return Fail(G4HB200_EINVAL, "null handle");
+  G4H_CUDA(cudaSetDevice(h->device));
+  return 0;
+}
+
+G4HB200SecondaryQueue NullQueue() {
+  G4HB200SecondaryQueue q;
+  std::memset(&q, 0, sizeof(q));
+  return q;
+}
+
+template <int kMode>
+int LaunchElectron(G4HB200* h, G4HB200ElectronBatch* dev, G4HB200SecondaryQueue* sec, uint64_t seed, void* stream) {
+  int rc = CheckHandle(h);
+  if (rc != 0) return rc;
+  if (dev == nullptr || dev->n < 0) return Fail(G4HB200_EINVAL, "bad electron batch");
+  if (kMode != 0 && sec == nullptr) return Fail(G4HB200_EINVAL, "secondary queue required");
+  if (dev->n == 0) return 0;
+  const G4HB200SecondaryQueue q = sec != nullptr ? *sec : NullQueue();
+  const int grid = GridFor(dev->n, h->smCount, 8);
+  ElectronKernel<kMode><<<grid, kThreadsPerBlock, 0, static_cast<cudaStream_t>(stream)>>>(h->view, *dev, q, seed);
+  ++h->launches;
+  G4H_CUDA(cudaGetLastError());
+  return 0;
+}
+
+template <int kMode>
+int LaunchGamma(G4HB200* h, G4HB200GammaBatch* dev, G4HB200SecondaryQueue* sec, uint64_t seed, void* stream) {
+  int rc = CheckHandle(h);
+  if (rc != 0) return rc;
+  if (dev == nullptr || dev->n < 0) return Fail(G4HB200_EINVAL, "bad gamma batch");
+  if (kMode != 0 && sec == nullptr) return Fail(G4HB200_EINVAL, "secondary queue required");
+  if (dev->n == 0) return 0;
+  const G4HB200SecondaryQueue q = sec != nullptr ? *sec : NullQueue();
+  const int grid = GridFor(dev->n, h->smCount, 8);
+  GammaKernel<kMode><<<grid, kThreadsPerBlock, 0, static_cast<cudaStream_t>(stream)>>>(h->view, *dev, q, seed);
+  ++h->launches;
+  G4H_CUDA(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* g4hb200_last_error(void) { return g_lastError.c_str(); }
+
+int g4hb200_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  return n;
+}
+
+int g4hb200_create(const G4HB200Tables* tables, int device, G4HB200** out) {
+  if (tables == nullptr || out == nullptr) return Fail(G4HB200_EINVAL, "null argument");
+  if (tables->num_matcut <= 0 || tables->num_mat <= 0 || tables->num_regions <= 0)
+    return Fail(G4HB200_EINVAL, "empty table set");
+  if (tables->electron.num_loss < 2 || tables->positron.num_loss < 2) return Fail(G4HB200_EINVAL, "bad e-loss grid");
+  for (int i = 0; i < tables->num_matcut; ++i) {
+    if (tables->mc_imat[i] < 0 || tables->mc_imat[i] >= tables->num_mat || tables->mc_ireg[i] < 0 ||
+        tables->mc_ireg[i] >= tables->num_regions)
+      return Fail(G4HB200_EINVAL, "couple refers to an unknown material / region");
+  }
+  if (g4hb200_device_count() <= 0) return Fail(G4HB200_ENODEVICE, "no CUDA device");
+  G4H_CUDA(cudaSetDevice(device));
+  G4HB200* h = new (std::nothrow) G4HB200;
+  if (h == nullptr) return Fail(G4HB200_ENOMEM, "host allocation");
+  h->device = device;
+  cudaDeviceProp prop;
+  G4H_CUDA(cudaGetDeviceProperties(&prop, device));
+  h->smCount = prop.multiProcessorCount;
+  h->desc = *tables;
+  G4HB200Tables& d = h->desc;
+  ArenaBuilder ab;
+  const int nmc = d.num_matcut, nmat = d.num_mat;
+  int nElemTot = 0;
+  for (int i = 0; i < nmat; ++i) nElemTot += tables->mat_num_elem[i];
+  ab.Add(d.region_pars, static_cast<size_t>(8) * d.num_regions);
+  ab.Add(d.mc_cuts, static_cast<size_t>(4) * nmc);
+  ab.Add(d.mc_imat, nmc);
+  ab.Add(d.mc_ireg, nmc);
+  ab.Add(d.mat_num_elem, nmat);
+  ab.Add(d.mat_elem_start, nmat);
+  ab.Add(d.mat_elem_z, nElemTot);
+  ab.Add(d.mat_elem_natoms, nElemTot);
+  ab.Add(d.mat_pars, static_cast<size_t>(16) * nmat);
+  ab.Add(d.mat_sandia_num, nmat);
+  ab.Add(d.mat_sandia_start, nmat);
+  ab.Add(d.elem_pars, static_cast<size_t>(12) * 121);
+  ab.Add(d.elem_sandia_num, 121);
+  ab.Add(d.elem_sandia_start, 121);
+  ab.Add(d.sandia_energies, d.num_sandia);
+  ab.Add(d.sandia_cof, static_cast<size_t>(4) * d.num_sandia);
+  AddElectron(ab, d.electron, nmc, nmat);
+  AddElectron(ab, d.positron, nmc, nmat);
+  ab.Add(d.sb_el_energy, 65);
+  ab.Add(d.sb_lel_energy, 65);
+  ab.Add(d.sb_lkappa, 54);
+  ab.Add(d.sb_gcut_start, nmc);
+  ab.Add(d.sb_gcut_indices, d.num_sb_gcut);
+  ab.Add(d.sb_start_per_z, 121);
+  ab.Add(d.sb_data, d.num_sb_data);
+  ab.Add(d.gm_mxsec, static_cast<size_t>(nmat) * d.gm_data_per_mat);
+  ab.Add(d.gm_conv_start, nmat);
+  ab.Add(d.gm_conv_egrid, d.gm_conv_egrid_size);
+  ab.Add(d.gm_conv_data, d.num_gm_conv);
+  // one allocation, one staged copy
+  h->arenaBytes = ab.total + 256;
+  {
+    const cudaError_t err = cudaMalloc(&h->arena, h->arenaBytes);
+    if (err != cudaSuccess) {
+      delete h;
+      return Fail(G4HB200_ENOMEM, "cudaMalloc(arena)", err);
+    }
+  }
+  std::vector<unsigned char> staging(h->arenaBytes, 0);
+  for (const auto& p : ab.pieces) {
+    std::memcpy(staging.data() + p.offset, p.src, p.bytes);
+    *p.dst = static_cast<unsigned char*>(h->arena) + p.offset;
+  }
+  {
+    const cudaError_t err = cudaMemcpy(h->arena, staging.data(), h->arenaBytes, cudaMemcpyHostToDevice);
+    if (err != cudaSuccess) {
+      cudaFree(h->arena);
+      delete h;
+      return Fail(G4HB200_ECUDA, "cudaMemcpy(arena)", err);
+    }
+  }
+  h->view = MakeView(d);
+  G4H_CUDA(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+  std::memset(&h->elDev, 0, sizeof(h->elDev));
+  std::memset(&h->gmDev, 0, sizeof(h->gmDev));
+  std::memset(&h->secDev, 0, sizeof(h->secDev));
+  *out = h;
+  return 0;
+}
+
+int g4hb200_destroy(G4HB200* h) {
+  if (h == nullptr) return 0;
+  cudaSetDevice(h->device);
+  if (h->elCap > 0) g4hb200_electron_batch_free(h, &h->elDev);
+  if (h->gmCap > 0) g4hb200_gamma_batch_free(h, &h->gmDev);
+  if (h->secCap > 0) g4hb200_secondary_queue_free(h, &h->secDev);
+  if (h->stream != nullptr) cudaStreamDestroy(h->stream);
+  if (h->arena != nullptr) cudaFree(h->arena);
+  delete h;
+  return 0;
+}
+
+int g4hb200_electron_batch_alloc(G4HB200* h, int64_t capacity, G4HB200ElectronBatch* out) {
+  int rc = CheckHandle(h);
+  if (rc != 0) return rc;
+  if (out == nullptr || capacity < 0) return Fail(G4HB200_EINVAL, "bad argument");
+  std::memset(out, 0, sizeof(*out));
+  double** g[16];
+  ElectronDoubleGroups(out, g);
+  for (int i = 0; i < 16; ++i) {
+    rc = DevAlloc(*g[i], static_cast<size_t>(capacity) * 2);
+    if (rc != 0) return rc;
+  }
+  rc = DevAlloc(out->meta, static_cast<size_t>(capacity) * 4);
+  if (rc != 0) return rc;
+  rc = DevAlloc(out->winner, static_cast<size_t>(capacity));
+  if (rc != 0) return rc;
+  out->n = 0;
+  return 0;
+}
+
+int g4hb200_electron_batch_free(G4HB200* h, G4HB200ElectronBatch* dev) {
+  int rc = CheckHandle(h);
+  if (rc != 0) return rc;
+  if (dev == nullptr) return 0;
+  double** g[16];
+  ElectronDoubleGroups(dev, g);
+  for (int i = 0; i < 16; ++i) cudaFree(*g[i]);
+  cudaFree(dev->meta);
+  cudaFree(dev->winner);
+  std::memset(dev, 0, sizeof(*dev));
+  return 0;
+}
+
+int g4hb200_gamma_batch_alloc(G4HB200* h, int64_t capacity, G4HB200GammaBatch* out) {
+  int rc = CheckHandle(h);
+  if (rc != 0) return rc;
+  if (out == nullptr || capacity < 0) return Fail(G4HB200_EINVAL, "bad argument");
+  std::memset(out, 0, sizeof(*out));
+  double** g[5];
+  GammaDoubleGroups(out, g);
+  for (int i = 0; i < 5; ++i) {
+    rc = DevAlloc(*g[i], static_cast<size_t>(capacity) * 2);
+    if (rc != 0) return rc;
+  }
+  rc = DevAlloc(out->meta, static_cast<size_t>(capacity) * 4);
+  if (rc != 0) return rc;
+  rc = DevAlloc(out->winner, static_cast<size_t>(capacity));
+  if (rc != 0) return rc;
+  out->n = 0;
+  return 0;
+}
+
+int g4hb200_gamma_batch_free(G4HB200* h, G4HB200GammaBatch* dev) {
+  int rc = CheckHandle(h);
+  if (rc != 0) return rc;
+  if (dev == nullptr) return 0;
+  double** g[5];
+  GammaDoubleGroups(dev, g);
+  for (int i = 0; i < 5; ++i) cudaFree(*g[i]);
+  cudaFree(dev->meta);
+  cudaFree(dev->winner);
+  std::memset(dev, 0, sizeof(*dev));
+  return 0;
+}
+
+int g4hb200_secondary_queue_alloc(G4HB200* h, int64_t capacity, G4HB200SecondaryQueue* out) {
+  int rc = CheckHandle(h);
+  if (rc != 0) return rc;
+  if (out == nullptr || capacity < 0) return Fail(G4HB200_EINVAL, "bad argument");
+  std::memset(out, 0, sizeof(*out));
+  out->capacity = capacity;
+  if ((rc = DevAlloc(out->dirx_diry, static_cast<size_t>(capacity) * 2)) != 0) return rc;
+  if ((rc = DevAlloc(out->dirz_ekin, static_cast<size_t>(capacity) * 2)) != 0) return rc;
+  if ((rc = DevAlloc(out->parent_kind, static_cast<size_t>(capacity) * 2)) != 0) return rc;
+  if ((rc = DevAlloc(out->parent_slot, static_cast<size_t>(capacity) * 2)) != 0) return rc;
+  if ((rc = DevAlloc(out->count, 4)) != 0) return rc;
+  G4H_CUDA(cudaMemset(out->count, 0, 16));
+  return 0;
+}
+
+int g4hb200_secondary_queue_free(G4HB200* h, G4HB200SecondaryQueue* dev) {
+  int rc = CheckHandle(h);
+  if (rc != 0) return rc;
+  if (dev == nullptr) return 0;
+  cudaFree(dev->dirx_diry);
+  cudaFree(dev->dirz_ekin);
+  cudaFree(dev->parent_kind);
+  cudaFree(dev->parent_slot);
+  cudaFree(dev->count);
+  std::memset(dev, 0, sizeof(*dev));
+  return 0;
+}
+
+int g4hb200_secondary_queue_reset(G4HB200* h, G4HB200SecondaryQueue* dev, void* stream) {
+  int rc = CheckHandle(h);
+  if (rc != 0) return rc;
+  if (dev == nullptr || dev->count == nullptr) return Fail(G4HB200_EINVAL, "bad queue");
+  G4H_CUDA(cudaMemsetAsync(dev->count, 0, sizeof(int32_t), static_cast<cudaStream_t>(stream)));
+  return 0;
+}
+
+int g4hb200_electron_batch_upload(G4HB200* h, const G4HB200ElectronBatch* host, G4HB200ElectronBatch* dev, void* stream) {
+  int rc = CheckHandle(h);
+  if (rc != 0) return rc;
+  if (host == nullptr || dev == nullptr) return Fail(G4HB200_EINVAL, "null batch");
+  return CopyElectron(host, dev, cudaMemcpyHostToDevice, static_cast<cudaStream_t>(stream), 0, 16, true, true);
+}
+
+int g4hb200_electron_batch_download(G4HB200* h, const G4HB200ElectronBatch* dev, G4HB200ElectronBatch* host, void* stream) {
+  int rc = CheckHandle(h);
+  if (rc != 0) return rc;
+  if (host == nullptr || dev == nullptr) return Fail(G4HB200_EINVAL, "null batch");
+  return CopyElectron(dev, host, cudaMemcpyDeviceToHost, static_cast<cudaStream_t>(stream), 0, 16, true, true);
+}
+
+int g4hb200_gamma_batch_upload(G4HB200* h, const G4HB200GammaBatch* host, G4HB200GammaBatch* dev, void* stream) {
+  int rc = CheckHandle(h);
+  if (rc != 0) return rc;
+  if (host == nullptr || dev == nullptr) return Fail(G4HB200_EINVAL, "null batch");
+  return CopyGamma(host, dev, cudaMemcpyHostToDevice, static_cast<cudaStream_t>(stream), 0, 5, true, true);
+}
+
+int g4hb200_gamma_batch_download(G4HB200* h, const G4HB200GammaBatch* dev, G4HB200GammaBatch* host, void* stream) {
+  int rc = CheckHandle(h);
+  if (rc != 0) return rc;
+  if (host == nullptr || dev == nullptr) return Fail(G4HB200_EINVAL, "null batch");
+  return CopyGamma(dev, host, cudaMemcpyDeviceToHost, static_cast<cudaStream_t>(stream), 0, 5, true, true);
+}
+
+int g4hb200_secondary_queue_download(G4HB200* h, const G4HB200SecondaryQueue* dev, G4HB200SecondaryQueue* host, void* stream) {
+  int rc = CheckHandle(h);
+  if (rc != 0) return rc;
+  if (host == nullptr || dev == nullptr) return Fail(G4HB200_EINVAL, "null queue");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  G4H_CUDA(cudaMemcpyAsync(host->count, dev->count, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+  G4H_CUDA(cudaStreamSynchronize(st));
+  int64_t n = host->count[0];
+  if (n > dev->capacity) {
+    host->count[0] = static_cast<int32_t>(dev->capacity);
+    return Fail(G4HB200_ECAPACITY, "secondary queue overflow on the device");
+  }
+  if (n > host->capacity) return Fail(G4HB200_ECAPACITY, "host secondary queue too small");
+  G4H_CUDA(cudaMemcpyAsync(host->dirx_diry, dev->dirx_diry, static_cast<size_t>(n) * 16, cudaMemcpyDeviceToHost, st));
+  G4H_CUDA(cudaMemcpyAsync(host->dirz_ekin, dev->dirz_ekin, static_cast<size_t>(n) * 16, cudaMemcpyDeviceToHost, st));
+  G4H_CUDA(cudaMemcpyAsync(host->parent_kind, dev->parent_kind, static_cast<size_t>(n) * 8, cudaMemcpyDeviceToHost, st));
+  G4H_CUDA(cudaMemcpyAsync(host->parent_slot, dev->parent_slot, static_cast<size_t>(n) * 8, cudaMemcpyDeviceToHost, st));
+  return 0;
+}
+
+int g4hb200_sync(G4HB200* h, void* stream) {
+  int rc = CheckHandle(h);
+  if (rc != 0) return rc;
+  G4H_CUDA(cudaStreamSynchronize(static_cast<cudaStream_t>(stream)));
+  return 0;
+}
+
+int g4hb200_electron_lookups(G4HB200* h, int64_t n, const int32_t* imc, const double* ekin, const double* logekin,
+                             int is_electron, double* out, void* stream) {
+  int rc = CheckHandle(h);
+  if (rc != 0) return rc;
+  if (n < 0 || (n > 0 && (!imc || !ekin || !logekin || !out))) return Fail(G4HB200_EINVAL, "bad argument");
+  if (n == 0) return 0;
+  ElectronLookupsKernel<<<GridFor(n, h->smCount, 8), kThreadsPerBlock, 0, static_cast<cudaStream_t>(stream)>>>(
+      h->view, n, imc, ekin, logekin, is_electron ? 0 : 1, out);
+  ++h->launches;
+  G4H_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int g4hb200_electron_stepping_xsecs(G4HB200* h, int64_t n, const int32_t* imc, const double* ekin, const double* logekin,
+                                    int is_electron, double* out, void* stream) {
+  int rc = CheckHandle(h);
+  if (rc != 0) return rc;
+  if (n < 0 || (n > 0 && (!imc || !ekin || !logekin || !out))) return Fail(G4HB200_EINVAL, "bad argument");
+  if (n == 0) return 0;
+  ElectronSteppingXSecsKernel<<<GridFor(n, h->smCount, 8), kThreadsPerBlock, 0, static_cast<cudaStream_t>(stream)>>>(
+      h->view, n, imc, ekin, logekin, is_electron ? 0 : 1, out);
+  ++h->launches;
+  G4H_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int g4hb200_gamma_lookups(G4HB200* h, int64_t n, const int32_t* imc, const double* ekin, const double* logekin,
+                          const double* urnd, double* out_mxsec, int32_t* out_pid, void* stream) {
+  int rc = CheckHandle(h);
+  if (rc != 0) return rc;
+  if (n < 0 || (n > 0 && (!imc || !ekin || !logekin || !urnd || !out_mxsec || !out_pid))) return Fail(G4HB200_EINVAL, "bad argument");
+  if (n == 0) return 0;
+  GammaLookupsKernel<<<GridFor(n, h->smCount, 8), kThreadsPerBlock, 0, static_cast<cudaStream_t>(stream)>>>(
+      h->view, n, imc, ekin, logekin, urnd, out_mxsec, out_pid);
+  ++h->launches;
+  G4H_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int g4hb200_select_target_element(G4HB200* h, int kind, int is_electron, int64_t n, const int32_t* imc,
+                                  const double* ekin, const double* logekin, const double* urnd, int32_t* out_elem,
+                                  void* stream) {
+  int rc = CheckHandle(h);
+  if (rc != 0) return rc;
+  if (kind < 0 || kind > 2 || n < 0 || (n > 0 && (!imc || !ekin || !logekin || !urnd || !out_elem)))
+    return Fail(G4HB200_EINVAL, "bad argument");
+  if (n == 0) return 0;
+  SelectTargetElementKernel<<<GridFor(n, h->smCount, 8), kThreadsPerBlock, 0, static_cast<cudaStream_t>(stream)>>>(
+      h->view, kind, is_electron ? 0 : 1, n, imc, ekin, logekin, urnd, out_elem);
+  ++h->launches;
+  G4H_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int g4hb200_vdt_log_exp(G4HB200* h, int64_t n, const double* x, double* out_log, double* out_exp, void* stream) {
+  int rc = CheckHandle(h);
+  if (rc != 0) return rc;
+  if (n < 0 || (n > 0 && (!x || !out_log || !out_exp))) return Fail(G4HB200_EINVAL, "bad argument");
+  if (n == 0) return 0;
+  VdtLogExpKernel<<<GridFor(n, h->smCount, 8), kThreadsPerBlock, 0, static_cast<cudaStream_t>(stream)>>>(n, x, out_log, out_exp);
+  ++h->launches;
+  G4H_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int g4hb200_rng_uniforms(G4HB200* h, uint64_t seed, int64_t n, const int32_t* track_id, int32_t ndraw, double* out,
+                         void* stream) {
+  int rc = CheckHandle(h);
+  if (rc != 0) return rc;
+  if (n < 0 || ndraw < 0 || (n > 0 && (!track_id || !out))) return Fail(G4HB200_EINVAL, "bad argument");
+  if (n == 0 || ndraw == 0) return 0;
+  RngUniformsKernel<<<GridFor(n, h->smCount, 8), kThreadsPerBlock, 0, static_cast<cudaStream_t>(stream)>>>(seed, n, track_id, ndraw, out);
+  ++h->launches;
+  G4H_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int g4hb200_electron_howfar(G4HB200* h, G4HB200ElectronBatch* dev, uint64_t seed, void* stream) {
+  return LaunchElectron<0>(h, dev, nullptr, seed, stream);
+}
+int g4hb200_electron_perform(G4HB200* h, G4HB200ElectronBatch* dev, G4HB200SecondaryQueue* sec, uint64_t seed, void* stream) {
+  return LaunchElectron<1>(h, dev, sec, seed, stream);
+}
+int g4hb200_electron_step(G4HB200* h, G4HB200ElectronBatch* dev, G4HB200SecondaryQueue* sec, uint64_t seed, void* stream) {
+  return LaunchElectron<2>(h, dev, sec, seed, stream);
+}
+int g4hb200_gamma_howfar(G4HB200* h, G4HB200GammaBatch* dev, uint64_t seed, void* stream) {
+  return LaunchGamma<0>(h, dev, nullptr, seed, stream);
+}
+int g4hb200_gamma_perform(G4HB200* h, G4HB200GammaBatch* dev, G4HB200SecondaryQueue* sec, uint64_t seed, void* stream) {
+  return LaunchGamma<1>(h, dev, sec, seed, stream);
+}
+int g4hb200_gamma_step(G4HB200* h, G4HB200GammaBatch* dev, G4HB200SecondaryQueue* sec, uint64_t seed, void* stream) {
+  return LaunchGamma<2>(h, dev, sec, seed, stream);
+}
+
+int g4hb200_electron_step_host(G4HB200* h, G4HB200ElectronBatch* host, G4HB200SecondaryQueue* hostSec, uint64_t seed) {
+  int rc = CheckHandle(h);
+  if (rc != 0) return rc;
+  if (host == nullptr || hostSec == nullptr) return Fail(G4HB200_EINVAL, "null argument");
+  const int64_t n = host->n;
+  if (n > h->elCap) {
+    if (h->elCap > 0) g4hb200_electron_batch_free(h, &h->elDev);
+    h->elCap = 0;
+    if ((rc = g4hb200_electron_batch_alloc(h, n, &h->elDev)) != 0) return rc;
+    h->elCap = n;
+  }
+  if (hostSec->capacity > h->secCap) {
+    if (h->secCap > 0) g4hb200_secondary_queue_free(h, &h->secDev);
+    h->secCap = 0;
+    if ((rc = g4hb200_secondary_queue_alloc(h, hostSec->capacity, &h->secDev)) != 0) return rc;
+    h->secCap = hostSec->capacity;
+  }
+  cudaStream_t st = h->stream;
+  // H2D: the 7 persistent groups + meta (128 B / track)
+  if ((rc = CopyElectron(host, &h->elDev, cudaMemcpyHostToDevice, st, 0, 7, true, false)) != 0) return rc;
+  if ((rc = g4hb200_secondary_queue_reset(h, &h->secDev, st)) != 0) return rc;
+  if ((rc = LaunchElectron<2>(h, &h->elDev, &h->secDev, seed, st)) != 0) return rc;
+  // D2H: persistent + result groups + meta + winner (180 B / track) and the secondaries
+  if ((rc = CopyElectron(&h->elDev, host, cudaMemcpyDeviceToHost, st, 0, 10, true, true)) != 0) return rc;
+  if ((rc = g4hb200_secondary_queue_download(h, &h->secDev, hostSec, st)) != 0) return rc;
+  G4H_CUDA(cudaStreamSynchronize(st));
+  return 0;
+}
+
+int g4hb200_gamma_step_host(G4HB200* h, G4HB200GammaBatch* host, G4HB200SecondaryQueue* hostSec, uint64_t seed) {
+  int rc = CheckHandle(h);
+  if (rc != 0) return rc;
+  if (host == nullptr || hostSec == nullptr) return Fail(G4HB200_EINVAL, "null argument");
+  const int64_t n = host->n;
+  if (n > h->gmCap) {
+    if (h->gmCap > 0) g4hb200_gamma_batch_free(h, &h->gmDev);
+    h->gmCap = 0;
+    if ((rc = g4hb200_gamma_batch_alloc(h, n, &h->gmDev)) != 0) return rc;
+    h->gmCap = n;
+  }
+  if (hostSec->capacity > h->secCap) {
+    if (h->secCap > 0) g4hb200_secondary_queue_free(h, &h->secDev);
+    h->secCap = 0;
+    if ((rc = g4hb200_secondary_queue_alloc(h, hostSec->capacity, &h->secDev)) != 0) return rc;
+    h->secCap = hostSec->capacity;
+  }
+  cudaStream_t st = h->stream;
+  if ((rc = CopyGamma(host, &h->gmDev, cudaMemcpyHostToDevice, st, 0, 3, true, false)) != 0) return rc;
+  if ((rc = g4hb200_secondary_queue_reset(h, &h->secDev, st)) != 0) return rc;
+  if ((rc = LaunchGamma<2>(h, &h->gmDev, &h->secDev, seed, st)) != 0) return rc;
+  if ((rc = CopyGamma(&h->gmDev, host, cudaMemcpyDeviceToHost, st, 0, 5, true, true)) != 0) return rc;
+  if ((rc = g4hb200_secondary_queue_download(h, &h->secDev, hostSec, st)) != 0) return rc;
+  G4H_CUDA(cudaStreamSynchronize(st));
+  return 0;
+}
+
+int64_t g4hb200_launch_count(const G4HB200* h) { return h != nullptr ? h->launches : 0; }
+
+}  // extern "C"

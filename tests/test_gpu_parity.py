@@ -1,0 +1,336 @@
+"""GPU parity: the CUDA kernels, called through the C-ABI, against the unmodified reference on the
+same tables, the same seeded track batches and the same injected uniform streams.
+
+Bar (BASELINE.json north_star): winner process, element / process indices, flags, uniform counts and
+secondary counts bit exact; energies, step lengths, directions within 1e-12 relative (tests/compare.py).
+"""
+import numpy as np
+import pytest
+
+from g4hepem_b200 import _capi, batches
+from tests import compare
+
+pytestmark = pytest.mark.gpu
+
+SEED = 2026
+
+
+def _cuda(a):
+    import torch
+
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+def test_vdt_log_exp_bit_exact(engine, reference):
+    rng = np.random.default_rng(1)
+    n = 1 << 20
+    x = np.exp(rng.uniform(np.log(1e-300), np.log(1e300), n))
+    x[:8] = [1.0, 2.0, 0.5, 1e-310, 0.70710678118654752440, 0.7071067811865476, 1e308, 5e-324]
+    lo, _ = engine.vdt_log_exp(_cuda(x))
+    assert np.array_equal(reference.vdt_log_exp(x)[0], lo.cpu().numpy())
+    xe = rng.uniform(-720, 720, n)
+    xe[:6] = [0.0, -0.0, 708.0, -708.0, 709.0, -1e-300]
+    _, ex = engine.vdt_log_exp(_cuda(xe))
+    assert np.array_equal(reference.vdt_log_exp(xe)[1], ex.cpu().numpy())
+
+
+@pytest.mark.parametrize("is_electron", [True, False])
+def test_electron_lookups_config1_bit_exact(engine, reference, flat_tables, is_electron):
+    """BASELINE config 1: 1M lookups, energies log-uniform 2-5 % beyond the grids
+    (testing/ElectronXSections/src/Implementation.cc:47-74, testing/ElectronEnergyLoss/src/Implementation.cc:37-57)."""
+    rng = np.random.default_rng(0)
+    n = 1 << 20
+    imc = rng.integers(0, flat_tables.num_matcut, n).astype(np.int32)
+    ek = np.exp(rng.uniform(np.log(0.95e-4), np.log(1.02e8), n))
+    lek = np.log(ek)
+    got = engine.electron_lookups(_cuda(imc), _cuda(ek), _cuda(lek), is_electron).cpu().numpy()
+    want = reference.electron_lookups(imc, ek, lek, is_electron)
+    assert np.array_equal(want, got)
+    got = engine.electron_stepping_xsecs(_cuda(imc), _cuda(ek), _cuda(lek), is_electron).cpu().numpy()
+    want = reference.electron_stepping_xsecs(imc, ek, lek, is_electron)
+    assert np.array_equal(want, got)
+
+
+def test_gamma_lookups_and_process_selection(engine, reference, flat_tables):
+    """testing/GammaXSections: total mac. xsec to 0 ulp and identical sampled process id."""
+    rng = np.random.default_rng(2)
+    n = 1 << 20
+    imc = rng.integers(0, flat_tables.num_matcut, n).astype(np.int32)
+    ek = np.exp(rng.uniform(np.log(0.98e-4), np.log(1.02e8), n))
+    lek = np.log(ek)
+    u = rng.uniform(size=n)
+    mx, pid = engine.gamma_lookups(_cuda(imc), _cuda(ek), _cuda(lek), _cuda(u))
+    wmx, wpid = reference.gamma_lookups(imc, ek, lek, u)
+    assert np.array_equal(wmx, mx.cpu().numpy())
+    assert np.array_equal(wpid, pid.cpu().numpy())
+
+
+def test_target_element_selectors(engine, reference, flat_tables):
+    """testing/ElectronTargetElementSelector, GammaTargetElementSelector: exact element index."""
+    rng = np.random.default_rng(4)
+    n = 1 << 18
+    ek = np.exp(rng.uniform(np.log(1e-3), np.log(1.02e8), n))
+    lek = np.log(ek)
+    u = rng.uniform(size=n)
+    couples = rng.choice(np.array([5, 6], dtype=np.int32), n).astype(np.int32)  # PbWO4, water
+    mats = rng.choice(np.array([3, 4], dtype=np.int32), n).astype(np.int32)
+    nelem = {5: 3, 6: 2, 3: 3, 4: 2}
+    for kind, idx in ((0, couples), (1, couples), (2, mats)):
+        for isel in (True, False):
+            got = engine.select_target_element(kind, isel, _cuda(idx), _cuda(ek), _cuda(lek), _cuda(u)).cpu().numpy()
+            want = reference.select_target_element(kind, isel, idx, ek, lek, u)
+            assert np.array_equal(want, got), (kind, isel)
+            assert all(got[idx == k].max() < v for k, v in nelem.items() if (idx == k).any())
+
+
+def _run_gpu_electron(engine, host, mode, n_sec=None):
+    import torch
+
+    from g4hepem_b200 import engine as eng
+
+    dev = eng.ElectronDeviceBatch(max(host.n, 1))
+    sec = eng.SecondaryDeviceQueue(n_sec if n_sec is not None else 2 * max(host.n, 1))
+    dev.upload(host)
+    if mode == "howfar":
+        eng.ElectronManager.HowFar(engine, dev, SEED)
+    elif mode == "perform":
+        eng.ElectronManager.Perform(engine, dev, sec, SEED)
+    else:
+        eng.ElectronManager.Step(engine, dev, sec, SEED)
+    torch.cuda.synchronize()
+    return dev.download(), sec
+
+
+def _assert_electron(want, got, qwant=None, qgot=None, handover=True):
+    rep = compare.compare_electron_batches(want, got, handover=handover)
+    assert compare.total_bad(rep) == 0, "\n" + compare.format_report(rep, True)
+    if qwant is not None:
+        srep = compare.compare_secondaries(qwant, qgot)
+        assert compare.total_bad(srep) == 0, "\n" + compare.format_report(srep, True)
+
+
+def test_electron_fused_step_config3(engine, reference, flat_tables):
+    """BASELINE config 3 shape at an oracle-sized n: e-/e+ 50/50, 1 keV-100 GeV, all couples."""
+    n = 400000
+    host = batches.make_electron_batch(n, flat_tables.num_matcut, seed=31)
+    want = host.copy()
+    qwant = batches.SecondaryHostQueue(2 * n)
+    reference.electron_step(want, qwant, SEED, 8)
+    got, sec = _run_gpu_electron(engine, host, "step")
+    _assert_electron(want, got, qwant, sec.download(), handover=False)
+
+
+def test_electron_howfar_then_perform_multi_step(engine, reference, flat_tables):
+    """HowFar and Perform as separate launches with a geometry stub in between, over several steps."""
+    import torch
+
+    from g4hepem_b200 import engine as eng
+
+    n = 100000
+    a = batches.make_electron_batch(n, flat_tables.num_matcut, seed=5)
+    dev = eng.ElectronDeviceBatch(n)
+    sec = eng.SecondaryDeviceQueue(2 * n)
+    dev.upload(a)
+    rng = np.random.default_rng(3)
+    for step in range(5):
+        qa = batches.SecondaryHostQueue(2 * n)
+        reference.electron_howfar(a, SEED, 8)
+        eng.ElectronManager.HowFar(engine, dev, SEED)
+        b = dev.download()
+        _assert_electron(a, b)
+        # geometry stub: 20 % of the steps are cut short and end on a boundary
+        cut = rng.uniform(size=n) < 0.2
+        f = rng.uniform(0.3, 1.0, n)
+        a.gstep_pstep[cut, 0] *= f[cut]
+        a.meta[:, 1] = np.where(cut, a.meta[:, 1] | _capi.F_ON_BOUNDARY, a.meta[:, 1] & ~_capi.F_ON_BOUNDARY)
+        # the GPU side gets the reference's (already compared) hand-over state: errors do not accumulate
+        dev.upload(a)
+        sec.reset()
+        reference.electron_perform(a, qa, SEED, 8)
+        eng.ElectronManager.Perform(engine, dev, sec, SEED)
+        torch.cuda.synchronize()
+        b = dev.download()
+        _assert_electron(a, b, qa, sec.download())
+        dead = a.ekin_logekin[:, 0] <= 0
+        a.ekin_logekin[dead, 0] = 1.0
+        a.ekin_logekin[dead, 1] = 100.0
+        dev.upload(a)
+
+
+def test_electron_free_running_steps_stay_in_tolerance(engine, reference, flat_tables):
+    """No re-synchronisation between steps: GPU state feeds the next GPU step."""
+    import torch
+
+    from g4hepem_b200 import engine as eng
+
+    n = 50000
+    a = batches.make_electron_batch(n, flat_tables.num_matcut, seed=77, emax=1.0e3)
+    dev = eng.ElectronDeviceBatch(n)
+    sec = eng.SecondaryDeviceQueue(2 * n)
+    dev.upload(a)
+    for step in range(4):
+        qa = batches.SecondaryHostQueue(2 * n)
+        reference.electron_step(a, qa, SEED, 8)
+        sec.reset()
+        eng.ElectronManager.Step(engine, dev, sec, SEED)
+        torch.cuda.synchronize()
+        b = dev.download()
+        # discrete quantities must stay identical, reals within tolerance
+        assert np.array_equal(a.winner, b.winner)
+        assert np.array_equal(a.meta, b.meta)
+        _assert_electron(a, b, qa, sec.download(), handover=False)
+
+
+@pytest.mark.parametrize("n", [0, 1, 31, 32, 33, 257, 1000])
+def test_electron_ragged_sizes(engine, reference, flat_tables, n):
+    host = batches.make_electron_batch(n, flat_tables.num_matcut, seed=100 + n)
+    want = host.copy()
+    qwant = batches.SecondaryHostQueue(2 * max(n, 1))
+    if n:
+        reference.electron_step(want, qwant, SEED, 1)
+    got, sec = _run_gpu_electron(engine, host, "step")
+    if n:
+        _assert_electron(want, got, qwant, sec.download(), handover=False)
+    else:
+        assert int(sec.count[0].item()) == 0
+
+
+def test_single_couples_and_energy_corners(engine, reference, flat_tables):
+    """Every couple alone (warp-uniform tables) and the corners of the energy range."""
+    for imc in range(flat_tables.num_matcut):
+        for (emin, emax) in ((1.0e-3, 2.0e-3), (0.9e3, 1.1e3), (0.5e8, 1.0e8), (1.0e-4, 1.1e-3)):
+            n = 4096
+            host = batches.make_electron_batch(n, flat_tables.num_matcut, seed=imc, emin=emin, emax=emax, couples=[imc])
+            want = host.copy()
+            qwant = batches.SecondaryHostQueue(2 * n)
+            reference.electron_step(want, qwant, SEED, 4)
+            got, sec = _run_gpu_electron(engine, host, "step")
+            _assert_electron(want, got, qwant, sec.download(), handover=False)
+
+
+def test_gamma_step_config2(engine, reference, flat_tables):
+    import torch
+
+    from g4hepem_b200 import engine as eng
+
+    n = 400000
+    g = batches.make_gamma_batch(n, flat_tables.num_matcut, boundary_fraction=0.1, seed=21)
+    want = g.copy()
+    qwant = batches.SecondaryHostQueue(2 * n)
+    reference.gamma_step(want, qwant, SEED, 8)
+    dev = eng.GammaDeviceBatch(n)
+    sec = eng.SecondaryDeviceQueue(2 * n)
+    dev.upload(g)
+    eng.GammaManager.Step(engine, dev, sec, SEED)
+    torch.cuda.synchronize()
+    got = dev.download()
+    rep = compare.compare_gamma_batches(want, got)
+    assert compare.total_bad(rep) == 0, "\n" + compare.format_report(rep, True)
+    srep = compare.compare_secondaries(qwant, sec.download())
+    assert compare.total_bad(srep) == 0, "\n" + compare.format_report(srep, True)
+
+
+def test_gamma_howfar_then_perform(engine, reference, flat_tables):
+    import torch
+
+    from g4hepem_b200 import engine as eng
+
+    n = 100000
+    g = batches.make_gamma_batch(n, flat_tables.num_matcut, seed=9)
+    dev = eng.GammaDeviceBatch(n)
+    sec = eng.SecondaryDeviceQueue(2 * n)
+    dev.upload(g)
+    reference.gamma_howfar(g, SEED, 8)
+    eng.GammaManager.HowFar(engine, dev, SEED)
+    got = dev.download()
+    assert compare.total_bad(compare.compare_gamma_batches(g, got)) == 0
+    rng = np.random.default_rng(8)
+    onb = rng.uniform(size=n) < 0.3
+    g.gstep_mfp0[onb, 0] *= rng.uniform(0.1, 1.0, n)[onb]
+    g.meta[:, 1] = np.where(onb, _capi.F_ON_BOUNDARY, 0).astype(np.int32)
+    dev.upload(g)
+    qwant = batches.SecondaryHostQueue(2 * n)
+    reference.gamma_perform(g, qwant, SEED, 8)
+    eng.GammaManager.Perform(engine, dev, sec, SEED)
+    torch.cuda.synchronize()
+    got = dev.download()
+    rep = compare.compare_gamma_batches(g, got)
+    assert compare.total_bad(rep) == 0, "\n" + compare.format_report(rep, True)
+    assert compare.total_bad(compare.compare_secondaries(qwant, sec.download())) == 0
+
+
+def test_host_buffer_entry_point(engine, reference, flat_tables):
+    """g4hb200_electron_step_host / gamma_step_host: host buffers in, host buffers out."""
+    n = 50000
+    host = batches.make_electron_batch(n, flat_tables.num_matcut, seed=41)
+    want = host.copy()
+    qwant = batches.SecondaryHostQueue(2 * n)
+    reference.electron_step(want, qwant, SEED, 8)
+    qgot = batches.SecondaryHostQueue(2 * n)
+    engine.electron_step_host(host, qgot, SEED)
+    _assert_electron(want, host, qwant, qgot, handover=False)
+    g = batches.make_gamma_batch(n, flat_tables.num_matcut, seed=42)
+    gw = g.copy()
+    reference.gamma_step(gw, qwant := batches.SecondaryHostQueue(2 * n), SEED, 8)
+    qgot = batches.SecondaryHostQueue(2 * n)
+    engine.gamma_step_host(g, qgot, SEED)
+    assert compare.total_bad(compare.compare_gamma_batches(gw, g)) == 0
+    assert compare.total_bad(compare.compare_secondaries(qwant, qgot)) == 0
+
+
+def test_secondary_queue_overflow_is_reported(engine, flat_tables):
+    n = 20000
+    host = batches.make_electron_batch(n, flat_tables.num_matcut, seed=43)
+    tiny = batches.SecondaryHostQueue(16)
+    with pytest.raises(_capi.G4HB200Error):
+        engine.electron_step_host(host, tiny, SEED)
+
+
+def test_full_size_properties_config3(engine, flat_tables):
+    """1M-track batch (BASELINE size): properties that need no oracle.
+    * results do not depend on the batch order (streams are keyed by track id)
+    * energy balance per track: E_pre (+ 2 m_e c^2 for an annihilating e+) = E_post + E_dep + sum E_secondaries
+    * directions stay unit vectors, winner in [-2, 3], at most two secondaries per track"""
+    import torch
+
+    from g4hepem_b200 import engine as eng
+
+    n = 1 << 20
+    host = batches.make_electron_batch(n, flat_tables.num_matcut, seed=51)
+    perm = np.random.default_rng(0).permutation(n)
+    shuffled = host.copy()
+    for g in shuffled.groups() + ("meta", "winner"):
+        getattr(shuffled, g)[...] = getattr(host, g)[perm]
+    outs = []
+    for hb in (host, shuffled):
+        dev = eng.ElectronDeviceBatch(n)
+        sec = eng.SecondaryDeviceQueue(2 * n)
+        dev.upload(hb)
+        eng.ElectronManager.Step(engine, dev, sec, SEED)
+        torch.cuda.synchronize()
+        outs.append((dev.download(), sec.download()))
+    (a, qa), (b, qb) = outs
+    for g in a.groups()[:10] + ("meta", "winner"):
+        assert np.array_equal(getattr(a, g)[perm], getattr(b, g), equal_nan=True), g
+    ra, rb = qa.sorted_records(), qb.sorted_records()
+    assert len(ra["ekin"]) == len(rb["ekin"])
+    order_a = np.lexsort((ra["slot"], ra["parent_id"]))
+    order_b = np.lexsort((rb["slot"], rb["parent_id"]))
+    assert np.array_equal(ra["ekin"][order_a], rb["ekin"][order_b])
+    # energy balance
+    mc2 = 0.51099890999999997
+    e_pre = host.ekin_logekin[:, 0]
+    e_post = a.ekin_logekin[:, 0]
+    edep = a.edep_dispx[:, 0]
+    esec = np.bincount(ra["parent_index"], weights=ra["ekin"], minlength=n)
+    nsec = np.bincount(ra["parent_index"], minlength=n)
+    is_pos = (host.meta[:, 1] & _capi.F_POSITRON) != 0
+    two_gamma = is_pos & (nsec == 2)
+    balance = e_pre + np.where(two_gamma, 2.0 * mc2, 0.0) - (e_post + edep + esec)
+    assert np.all(np.abs(balance) <= 1e-9 * np.maximum(e_pre, 1.0)), np.abs(balance).max()
+    assert nsec.max() <= 2
+    assert a.winner.min() >= -2 and a.winner.max() <= 3
+    d = np.stack([a.dirx_diry[:, 0], a.dirx_diry[:, 1], a.dirz_safety[:, 0]], axis=1)
+    assert np.all(np.abs(np.linalg.norm(d, axis=1) - 1.0) < 1e-9)
+    sd = np.linalg.norm(ra["dir"], axis=1)
+    assert np.all(np.abs(sd - 1.0) < 1e-9)

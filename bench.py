@@ -1,0 +1,351 @@
+#!/usr/bin/env python
+"""bench.py -- the hot path's headline measurement (contract: one JSON line on stdout from rank 0).
+
+    python bench.py --gpus 1 --steps 20 --warmup 3
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+        bench.py --gpus N --steps K --warmup W
+    python bench.py --impl reference --gpus 1 --steps 5 --warmup 1
+
+Workload (BASELINE.json configs[2], the one the north-star target "e- HowFar+Perform track-steps/s per B200"
+is quoted on): a batch of 1M e-/e+ tracks, 50/50, E log-uniform 1 keV-100 GeV, couples uniform over the table
+set, isotropic directions, safety U[0,1mm], 10 % on a boundary, first-step state.  One "step" = one fused
+HowFar + Perform pass (g4hb200_electron_step) over one such batch = 1M track-steps.  Every step of the timed
+region gets its own pristine device batch out of a ring (K x 276 MB >> the 126 MB L2, so inputs are always
+cold and every step does the same work); at N GPUs every rank owns its own ring (weak scaling, no data-path
+collective; one tiny allreduce of the deposited-energy sum after the timed region, as TestEm3's Run::Merge).
+
+`value`   : device-resident track-steps/s (CUDA events on the launch stream, max over ranks).
+`e2e`     : the same metric through the host-buffer C-ABI call g4hb200_electron_step_host with pinned HOST
+            batches: H2D of the persistent groups, the kernel, D2H of state + results + secondaries, per step.
+`roofline`: HBM; algorithmic bytes = 128 B read + 180 B written per track-step + 48 B per secondary.
+`cpu_baseline` / `--impl reference`: the unmodified reference (oracle/_ref) on the host cores, same batch.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+STATE_JSON = os.path.join(ROOT, "tests", "golden", "hepem_state.json")
+SEED = 2026
+METRIC = "e-/e+ HowFar+Perform track-steps/s"
+UNIT = "track-steps/s"
+READ_BYTES = 7 * 16 + 16           # 7 persistent pair groups + meta
+WRITE_BYTES = 10 * 16 + 16 + 4     # persistent + 3 result groups + meta + winner
+SEC_BYTES = 16 + 16 + 8 + 8        # one secondary record
+
+
+def _workload_config(n_tracks, ring):
+    return {
+        "workload": "BASELINE configs[2]: e-/e+ fused HowFar+Perform step (eloss fluctuation, Urban MSC, "
+                    "Moller/Bhabha, SB+RB brem, annihilation), 50/50 e-/e+, E log-uniform 1 keV-100 GeV",
+        "tracks_per_step_per_gpu": n_tracks,
+        "couples": "synthetic ATLASbar-shaped set (Galactic, Pb, lAr x2 regions) + PbWO4 + water, "
+                   "tests/golden/hepem_state.json",
+        "cache": f"each timed step reads its own pristine {n_tracks}-track batch from a ring of {ring} "
+                 "(inputs larger than L2)",
+        "seed": SEED,
+    }
+
+
+def _peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    QUERY = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.tmp = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.proc = None
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(index), f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=self.tmp, stderr=subprocess.DEVNULL)
+        except OSError:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if self.proc is None:
+            return out
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        self.tmp.flush()
+        self.tmp.seek(0)
+        sm, smax, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in self.tmp.read().splitlines():
+            parts = [p.strip() for p in line.split(",")]
+            if len(parts) < 6:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                smax.append(float(parts[1]))
+            except ValueError:
+                continue
+            for name, val in zip(names, parts[2:6]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        self.tmp.close()
+        os.unlink(self.tmp.name)
+        if sm:
+            out["sm_mhz"] = float(np.median(sm))
+            out["sm_max_mhz"] = float(max(smax))
+            out["samples"] = len(sm)
+        out["reasons"] = sorted(reasons)
+        return out
+
+
+def _dist_env():
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    return rank, world, local
+
+
+def _cpu_reference_rate(n_tracks, reps, id_offset=0):
+    """The unmodified reference's HowFar+Perform over the same batch on all host threads; best of `reps`."""
+    from g4hepem_b200 import batches, tables
+    from oracle import checker
+
+    ft = tables.load_state_json(STATE_JSON)
+    ora = checker.best_available(STATE_JSON)
+    threads = ora.hardware_threads() if hasattr(ora, "hardware_threads") else (os.cpu_count() or 1)
+    pristine = batches.make_electron_batch(n_tracks, ft.num_matcut, seed=SEED, id_offset=id_offset)
+    times = []
+    for _ in range(reps):
+        work = pristine.copy()
+        sec = batches.SecondaryHostQueue(2 * n_tracks)
+        t0 = time.perf_counter()
+        ora.electron_step(work, sec, SEED, threads)
+        times.append(time.perf_counter() - t0)
+    return n_tracks / min(times), threads, ora.kind, times
+
+
+def run_reference(args):
+    """--impl reference: the reference's own CPU implementation of the path, all host threads, rank 0 only."""
+    rank, world, _ = _dist_env()
+    if rank != 0:
+        return 0
+    n = args.tracks
+    from g4hepem_b200 import batches, tables
+    from oracle import checker
+
+    ft = tables.load_state_json(STATE_JSON)
+    ora = checker.best_available(STATE_JSON)
+    threads = ora.hardware_threads()
+    pristine = batches.make_electron_batch(n, ft.num_matcut, seed=SEED)
+    works = [pristine.copy() for _ in range(args.warmup + args.steps)]
+    secs = [batches.SecondaryHostQueue(2 * n) for _ in range(args.warmup + args.steps)]
+    for i in range(args.warmup):
+        ora.electron_step(works[i], secs[i], SEED, threads)
+    t0 = time.perf_counter()
+    for i in range(args.warmup, args.warmup + args.steps):
+        ora.electron_step(works[i], secs[i], SEED, threads)
+    dt = time.perf_counter() - t0
+    value = n * args.steps / dt
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": _workload_config(n, args.steps),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": ora.kind,
+                         "sample": f"{args.steps} passes of G4HepEmElectronManager::HowFar+Perform over the full {n}-track batch, "
+                                   f"std::thread x {threads}, wall clock"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+def run_gpu(args):
+    import torch
+
+    from g4hepem_b200 import batches, engine as eng, tables
+
+    rank, world, local = _dist_env()
+    if world != args.gpus and world > 1:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: g4hepem_b200 has no CPU fallback")
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    n = args.tracks
+    steps, warmup = args.steps, max(args.warmup, 3)
+    ft = tables.load_state_json(STATE_JSON)
+    engine = eng.Engine(ft, device=local)
+    pristine = batches.make_electron_batch(n, ft.num_matcut, seed=SEED, id_offset=rank * n, pinned=True)
+
+    # ---- device-resident ring: one pristine batch per step (warm-up steps get their own) ------------------
+    per_batch = n * (16 * 16 + 16 + 4)
+    ring_n = warmup + steps
+    if ring_n * per_batch > 100e9:
+        ring_n = max(4, int(100e9 // per_batch))
+    ring = []
+    for i in range(ring_n):
+        d = eng.ElectronDeviceBatch(n, device=local)
+        d.upload(pristine, groups=batches.ElectronHostBatch.PAIR_GROUPS + ("meta",))
+        ring.append(d)
+    sec = eng.SecondaryDeviceQueue(2 * n, device=local)
+    torch.cuda.synchronize()
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for i in range(warmup):
+        sec.reset()
+        eng.ElectronManager.Step(engine, ring[i % ring_n], sec, SEED)
+    barrier()
+    launches0 = engine.launch_count
+    sampler = ClockSampler(local) if rank == 0 else None
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+    barrier()
+    ev0.record()
+    for i in range(steps):
+        b = ring[(warmup + i) % ring_n]
+        sec.reset()
+        kev[i][0].record()
+        eng.ElectronManager.Step(engine, b, sec, SEED)
+        kev[i][1].record()
+    ev1.record()
+    barrier()
+    elapsed_ms = ev0.elapsed_time(ev1)
+    kernel_ms = float(np.mean([a.elapsed_time(b) for a, b in kev]))
+    n_sec = int(sec.count[0].item())
+    launches = engine.launch_count - launches0
+    clocks = sampler.stop() if sampler is not None else None
+    if dist is not None:
+        t = torch.tensor([elapsed_ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        elapsed_ms = float(t.item())
+    value = world * n * steps / (elapsed_ms * 1e-3)
+
+    # ---- the one collective of the path: sum of deposited energy over all ranks (cf. Run::Merge) --------------
+    edep = ring[(warmup + steps - 1) % ring_n].t["edep_dispx"][:n, 0].sum().reshape(1)
+    if dist is not None:
+        dist.all_reduce(edep)
+    edep_sum = float(edep.item())
+
+    # ---- e2e: host buffers through the C-ABI ---------------------------------------------------------------
+    e2e_steps = min(steps, args.e2e_steps)
+    work = batches.ElectronHostBatch(n, pinned=True)
+    hsec = batches.SecondaryHostQueue(2 * n, pinned=True)
+    in_groups = batches.ElectronHostBatch.PAIR_GROUPS + ("meta",)
+
+    def restore():
+        for g in in_groups:
+            getattr(work, g)[...] = getattr(pristine, g)
+
+    e2e_times = []
+    for i in range(2 + e2e_steps):
+        restore()
+        barrier()
+        t0 = time.perf_counter()
+        engine.electron_step_host(work, hsec, SEED)
+        dt = time.perf_counter() - t0
+        if i >= 2:
+            e2e_times.append(dt)
+    e2e_dt = float(np.sum(e2e_times))
+    if dist is not None:
+        t = torch.tensor([e2e_dt], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_dt = float(t.item())
+    e2e_value = world * n * e2e_steps / e2e_dt
+    n_sec_host = int(hsec.count[0])
+    h2d = n * READ_BYTES
+    d2h = n * WRITE_BYTES + n_sec_host * SEC_BYTES + 4
+
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return 0
+
+    peak, peak_src = _peaks()
+    alg_bytes = n * (READ_BYTES + WRITE_BYTES) + n_sec * SEC_BYTES
+    achieved = alg_bytes / (kernel_ms * 1e-3) / 1e9
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": warmup,
+        "ms_per_step": elapsed_ms / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic", "config": _workload_config(n, ring_n),
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "steps": e2e_steps, "api": "g4hb200_electron_step_host (pinned host batch in, host batch + secondaries out)"},
+        "gpu_launches": int(launches),
+        "clocks": clocks,
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "traffic": _traffic_from_profile(), "kernel": "g4h::ElectronKernel<2>", "kernel_ms": kernel_ms,
+                     "algorithmic_bytes_per_launch": alg_bytes, "peak_source": peak_src,
+                     "secondaries_per_launch": n_sec},
+        "edep_sum_mev_last_step_allreduced": edep_sum,
+    }
+    if not args.no_cpu_baseline and world == 1:
+        try:
+            v, threads, kind, times = _cpu_reference_rate(min(n, args.cpu_sample), 3)
+            line["cpu_baseline"] = {
+                "value": v, "unit": UNIT, "cores": threads, "kind": kind,
+                "sample": f"best of 3 passes of HowFar+Perform over {min(n, args.cpu_sample)} tracks of the same batch "
+                          f"({sum(times):.2f} s wall in total), std::thread x {threads}"}
+        except Exception as exc:  # the checker library is test infrastructure; its absence must not hide the GPU number
+            line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 0, "kind": "unavailable", "sample": str(exc)}
+    print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
+    return 0
+
+
+def _traffic_from_profile():
+    """dram bytes read+written per launch of the step kernel from the committed `ncu --set full` summary."""
+    path = os.path.join(ROOT, "profiles", "r01_electron_step_full.json")
+    if os.path.exists(path):
+        try:
+            with open(path) as f:
+                return json.load(f).get("dram_bytes_per_launch")
+        except (OSError, ValueError):
+            return None
+    return None
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--tracks", type=int, default=1 << 20, help="tracks per step per GPU (BASELINE: 1M)")
+    ap.add_argument("--e2e-steps", type=int, default=10)
+    ap.add_argument("--cpu-sample", type=int, default=1 << 20)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_gpu(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

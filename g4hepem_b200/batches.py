@@ -72,13 +72,23 @@ class GammaHostBatch(_HostBatch):
 
 
 class SecondaryHostQueue:
-    def __init__(self, capacity):
+    def __init__(self, capacity, pinned=False):
         self.capacity = int(capacity)
-        self.dirx_diry = np.zeros((self.capacity, 2))
-        self.dirz_ekin = np.zeros((self.capacity, 2))
-        self.parent_kind = np.zeros((self.capacity, 2), dtype=np.int32)
-        self.parent_slot = np.zeros((self.capacity, 2), dtype=np.int32)
-        self.count = np.zeros(1, dtype=np.int32)
+        self._torch = []
+        self.dirx_diry = self._alloc((self.capacity, 2), np.float64, pinned)
+        self.dirz_ekin = self._alloc((self.capacity, 2), np.float64, pinned)
+        self.parent_kind = self._alloc((self.capacity, 2), np.int32, pinned)
+        self.parent_slot = self._alloc((self.capacity, 2), np.int32, pinned)
+        self.count = self._alloc((4,), np.int32, pinned)[:1]
+
+    def _alloc(self, shape, dtype, pinned):
+        if pinned:
+            import torch
+
+            t = torch.zeros(shape, dtype=torch.float64 if dtype == np.float64 else torch.int32).pin_memory()
+            self._torch.append(t)
+            return t.numpy()
+        return np.zeros(shape, dtype=dtype)
 
     def as_struct(self):
         s = _capi.SecondaryQueue()

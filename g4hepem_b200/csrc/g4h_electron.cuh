@@ -418,7 +418,7 @@ G4H_FN double SampleCosineTheta(double pStepLength, double preStepEkin, double p
   const double dumEaa = 1. / (1. - dumEa);
   double thex = theta2 * (1.0 - theta2 * 0.0833333);
   if (theta2 > 0.01) {
-    const double dum = 2.0 * sin(0.5 * theta0);
+    const double dum = 2.0 * Sin(0.5 * theta0);
     thex = dum * dum;
   }
   const double xmean1 = 1. - (1. - (1. + parXsi) * dumEa) * thex * dumEaa;

@@ -70,6 +70,8 @@ ElectronKernel(const __grid_constant__ TablesView tv, const __grid_constant__ G4
       }
       StoreElectron(b, i, s, rng);
       if (kMode == 0) StoreElectronHandOver(b, i, s);
+      // Perform re-converts the geometrical step when geometry cut it (UpdatePStepLength): fTrueStepLength / fZPathLength
+      if (kMode == 1) StorePair(b.tstep_zpath, i, s.trueStep, s.zPath);
     }
     if (kMode != 0) {
       __syncwarp();

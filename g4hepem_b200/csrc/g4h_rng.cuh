@@ -23,65 +23,79 @@ G4H_FN uint32_t MulHi32(uint32_t a, uint32_t b) {
 #endif
 }
 
+struct Philox4 {
+  uint32_t x, y, z, w;
+};
+
+// Philox4x32-10 block: counter = {blk, 0, id, 0}, key = {k0, k1}
+G4H_LEAF Philox4 PhiloxBlock(uint32_t k0, uint32_t k1, uint32_t id, uint32_t blk) {
+  uint32_t x0 = blk, x1 = 0u, x2 = id, x3 = 0u;
+  uint32_t ka = k0, kb = k1;
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint32_t hi0 = MulHi32(0xD2511F53u, x0);
+    const uint32_t lo0 = 0xD2511F53u * x0;
+    const uint32_t hi1 = MulHi32(0xCD9E8D57u, x2);
+    const uint32_t lo1 = 0xCD9E8D57u * x2;
+    const uint32_t n0 = hi1 ^ x1 ^ ka;
+    const uint32_t n2 = hi0 ^ x3 ^ kb;
+    x0 = n0; x1 = lo1; x2 = n2; x3 = lo0;
+    ka += 0x9E3779B9u;
+    kb += 0xBB67AE85u;
+  }
+  return Philox4{x0, x1, x2, x3};
+}
+
+struct Uniform2 {
+  double a, b;
+};
+
+// (2k+1) * 2^-53 with k the top 52 bits of hi:lo -- exact: build 1.m in [1,2) and subtract (1 - 2^-53)
+G4H_FN double ToUniform(uint32_t lo, uint32_t hi) {
+  const uint64_t bits = (static_cast<uint64_t>(hi) << 32) | lo;
+  const double d = FromBits(0x3FF0000000000000ULL | (bits >> 12));
+  return d - 0.99999999999999988897769753748;  // 1 - 2^-53
+}
+
+// the two uniforms of block blk (draws 2*blk and 2*blk+1) of track id
+G4H_LEAF Uniform2 UniformPair(uint32_t k0, uint32_t k1, uint32_t id, uint32_t blk) {
+  const Philox4 r = PhiloxBlock(k0, k1, id, blk);
+  return Uniform2{ToUniform(r.x, r.y), ToUniform(r.z, r.w)};
+}
+
 struct Rng {
-  uint32_t k0, k1;     // key: global seed
-  uint32_t id;         // track id
-  uint32_t draw;       // index of the next uniform
-  uint32_t cachedBlk;  // block index whose second pair is cached (0xffffffff: none)
-  uint32_t c2, c3;     // cached words
-  bool hasGauss;       // G4HepEmRandomEngine::fIsGauss
-  double gauss;        // G4HepEmRandomEngine::fGauss
+  uint32_t k0, k1;  // key: global seed
+  uint32_t id;      // track id
+  uint32_t draw;    // index of the next uniform
+  bool hasNext;     // `next` holds the uniform with index `draw` (only ever true while draw is odd)
+  double next;
+  bool hasGauss;    // G4HepEmRandomEngine::fIsGauss
+  double gauss;     // G4HepEmRandomEngine::fGauss
 
   G4H_MFN void Init(uint64_t seed, uint32_t trackId, uint32_t firstDraw, bool isGauss, double gaussVal) {
     k0 = static_cast<uint32_t>(seed);
     k1 = static_cast<uint32_t>(seed >> 32);
     id = trackId;
     draw = firstDraw;
-    cachedBlk = 0xffffffffu;
-    c2 = c3 = 0u;
+    hasNext = false;
+    next = 0.0;
     hasGauss = isGauss;
     gauss = gaussVal;
   }
 
-  G4H_MFN static double ToUniform(uint32_t lo, uint32_t hi) {
-    // (2k+1) * 2^-53 with k the top 52 bits of hi:lo -- exact: build 1.m in [1,2) and subtract (1 - 2^-53)
-    const uint64_t bits = (static_cast<uint64_t>(hi) << 32) | lo;
-    const double d = FromBits(0x3FF0000000000000ULL | (bits >> 12));
-    return d - 0.99999999999999988897769753748;  // 1 - 2^-53
-  }
-
-  G4H_MFN void Block(uint32_t blk, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) const {
-    uint32_t x0 = blk, x1 = 0u, x2 = id, x3 = 0u;
-    uint32_t ka = k0, kb = k1;
-#pragma unroll
-    for (int r = 0; r < 10; ++r) {
-      const uint32_t hi0 = MulHi32(0xD2511F53u, x0);
-      const uint32_t lo0 = 0xD2511F53u * x0;
-      const uint32_t hi1 = MulHi32(0xCD9E8D57u, x2);
-      const uint32_t lo1 = 0xCD9E8D57u * x2;
-      const uint32_t n0 = hi1 ^ x1 ^ ka;
-      const uint32_t n2 = hi0 ^ x3 ^ kb;
-      x0 = n0; x1 = lo1; x2 = n2; x3 = lo0;
-      ka += 0x9E3779B9u;
-      kb += 0xBB67AE85u;
-    }
-    r0 = x0; r1 = x1; r2 = x2; r3 = x3;
-  }
-
-  // G4HepEmRandomEngine::flat()
+  // G4HepEmRandomEngine::flat(): draws are consumed strictly in order, so the second uniform of a block is
+  // always the next one asked for
   G4H_MFN double Flat() {
     const uint32_t j = draw++;
-    const uint32_t blk = j >> 1;
-    if (j & 1u) {
-      if (blk == cachedBlk) return ToUniform(c2, c3);
-      uint32_t r0, r1, r2, r3;
-      Block(blk, r0, r1, r2, r3);
-      return ToUniform(r2, r3);
+    if (hasNext) {
+      hasNext = false;
+      return next;
     }
-    uint32_t r0, r1;
-    Block(blk, r0, r1, c2, c3);
-    cachedBlk = blk;
-    return ToUniform(r0, r1);
+    const Uniform2 u = UniformPair(k0, k1, id, j >> 1);
+    if (j & 1u) return u.b;
+    next = u.b;
+    hasNext = true;
+    return u.a;
   }
 
   // G4HepEmRandomEngine::Gauss (G4HepEmRandomEngine.hh:50-67): polar Box-Muller, second variate cached
@@ -122,7 +136,7 @@ struct Rng {
     }
     const double u0 = Flat();
     const double u1 = Flat();
-    const double t = sqrt(-2. * Log(u0)) * cos(k2Pi * u1);
+    const double t = sqrt(-2. * Log(u0)) * Cos(k2Pi * u1);
     const double value = mean + t * sqrt(mean) + 0.5;
     return value < 0. ? 0 : value >= limit ? static_cast<int>(limit) : static_cast<int>(value);
   }

@@ -108,7 +108,7 @@ G4H_FN int LogBin(double logx, double logxmin, double invLDBin, int ndata) {
 }
 
 // GetSplineLog, y and second derivative interleaved, separate x grid (G4HepEmRunUtils.icc:86-93)
-G4H_FN double SplineLogYSD(int ndata, const double* xdata, const double* ydata, double x, double logx, double logxmin,
+G4H_LEAF double SplineLogYSD(int ndata, const double* xdata, const double* ydata, double x, double logx, double logxmin,
                            double invLDBin) {
   const double xv = Max(G4H_LD(xdata), Min(G4H_LD(xdata + ndata - 1), x));
   const int idx   = LogBin(logx, logxmin, invLDBin, ndata);
@@ -118,7 +118,7 @@ G4H_FN double SplineLogYSD(int ndata, const double* xdata, const double* ydata, 
 }
 
 // GetSplineLog, x, y and second derivative interleaved (G4HepEmRunUtils.icc:97-104)
-G4H_FN double SplineLogXYSD(int ndata, const double* data, double x, double logx, double logxmin, double invLDBin) {
+G4H_LEAF double SplineLogXYSD(int ndata, const double* data, double x, double logx, double logxmin, double invLDBin) {
   const double xv = Max(G4H_LD(data), Min(G4H_LD(data + 3 * (ndata - 1)), x));
   const int idx   = LogBin(logx, logxmin, invLDBin, ndata);
   const int idx3  = 3 * idx;
@@ -143,7 +143,7 @@ G4H_FN double RestDEDX(const ElectronTablesView& ed, int imc, double ekin, doubl
 
 // GetInvRange (.icc:504-519) with FindLowerBinIndex (G4HepEmRunUtils.icc:227-237) and the strided
 // GetSpline (G4HepEmRunUtils.icc:108-110)
-G4H_FN double InvRange(const ElectronTablesView& ed, int imc, double range) {
+G4H_LEAF double InvRange(const ElectronTablesView& ed, int imc, double range) {
   const int n = ed.numLoss;
   const double* rdata = ed.lossData + 5 * n * imc;
   const double minRange = G4H_LD(rdata);
@@ -220,7 +220,7 @@ G4H_FN double TransportMFP(const ElectronTablesView& ed, int imat, double ekin, 
 }
 
 // ComputeMacXsecAnnihilation (.icc:585-593): Heitler e+e- -> 2 gamma
-G4H_FN double MacXSecAnnihilation(double ekin, double electronDensity) {
+G4H_LEAF double MacXSecAnnihilation(double ekin, double electronDensity) {
   const double tau  = ekin * kInvElectronMassC2;
   const double gam  = tau + 1.0;
   const double gam2 = gam * gam;
@@ -304,7 +304,7 @@ G4H_FN double MacXSecPE(const TablesView& tv, int imat, double ekin) {
 
 // GetSplineLog4 with one selected column (G4HepEmRunUtils.icc:178-187); iwhich = 1..4 (5 reads one slot
 // past the PE column, exactly as the reference does when gamma-nuclear is probed)
-G4H_FN double SplineLog4(const double* data, double x, double logx, double logxmin, double invLDBin, int iwhich) {
+G4H_LEAF double SplineLog4(const double* data, double x, double logx, double logxmin, double invLDBin, int iwhich) {
   const int idx    = LogBin(logx, logxmin, invLDBin, 256);
   const int idx9_0 = 9 * idx;
   const int idx9_1 = idx9_0 + 9;

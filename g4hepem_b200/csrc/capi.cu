@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <string>
@@ -11,6 +12,7 @@
 
 #include "../../include/g4hepem_b200.h"
 #include "g4h_kernels.cuh"
+#include "g4h_pipeline.cuh"
 #include "g4h_view.cuh"
 
 using namespace g4h;
@@ -99,6 +101,11 @@ struct G4HB200 {
   G4HB200GammaBatch gmDev;
   G4HB200SecondaryQueue secDev;
   int64_t elCap = 0, gmCap = 0, secCap = 0;
+  // workspace of the pipelined Perform (interaction queues, pre-step energies)
+  ElectronWork elWork;
+  void* elWorkMem = nullptr;
+  int64_t elWorkCap = 0;
+  bool monolith = false;  // G4HB200_MONOLITH=1: the one-kernel-per-step variant (kept for A/B measurements)
 };
 
 namespace {
@@ -218,6 +225,63 @@ int LaunchGamma(G4HB200* h, G4HB200GammaBatch* dev, G4HB200SecondaryQueue* sec, 
   return 0;
 }
 
+// interaction queues + pre-step energies for n tracks: one allocation, carved up
+int EnsureElectronWork(G4HB200* h, int64_t n) {
+  if (n <= h->elWorkCap) return 0;
+  if (h->elWorkMem != nullptr) {
+    G4H_CUDA(cudaDeviceSynchronize());
+    cudaFree(h->elWorkMem);
+    h->elWorkMem = nullptr;
+    h->elWorkCap = 0;
+  }
+  const size_t cap = static_cast<size_t>((n + 255) & ~static_cast<int64_t>(255));
+  const size_t bytes = cap * 16 + static_cast<size_t>(kNumElQueues) * cap * 4 + 256;
+  const cudaError_t err = cudaMalloc(&h->elWorkMem, bytes);
+  if (err != cudaSuccess) return Fail(G4HB200_ENOMEM, "cudaMalloc(workspace)", err);
+  unsigned char* p = static_cast<unsigned char*>(h->elWorkMem);
+  h->elWork.prestep = reinterpret_cast<double*>(p);
+  p += cap * 16;
+  for (int k = 0; k < kNumElQueues; ++k) {
+    h->elWork.queue[k] = reinterpret_cast<int32_t*>(p);
+    p += cap * 4;
+  }
+  h->elWork.count = reinterpret_cast<int32_t*>(p);
+  h->elWorkCap = static_cast<int64_t>(cap);
+  return 0;
+}
+
+// G4HepEmElectronManager::Perform as a pipeline (g4h_pipeline.cuh); kFused: HowFar first
+template <bool kFused>
+int LaunchElectronPipeline(G4HB200* h, G4HB200ElectronBatch* dev, G4HB200SecondaryQueue* sec, uint64_t seed, void* stream) {
+  int rc = CheckHandle(h);
+  if (rc != 0) return rc;
+  if (dev == nullptr || dev->n < 0) return Fail(G4HB200_EINVAL, "bad electron batch");
+  if (sec == nullptr) return Fail(G4HB200_EINVAL, "secondary queue required");
+  if (dev->n == 0) return 0;
+  if (dev->n > 0x7fffffff) return Fail(G4HB200_EINVAL, "batch too large (track indices are 32 bit)");
+  if ((rc = EnsureElectronWork(h, dev->n)) != 0) return rc;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int grid = GridFor(dev->n, h->smCount, 8);
+  const ElectronWork& w = h->elWork;
+  G4H_CUDA(cudaMemsetAsync(w.count, 0, kNumElQueues * sizeof(int32_t), st));
+  if (kFused) {
+    ElectronKernel<0><<<grid, kThreadsPerBlock, 0, st>>>(h->view, *dev, NullQueue(), seed);
+    ++h->launches;
+  }
+  ElContinuousKernel<<<grid, kThreadsPerBlock, 0, st>>>(h->view, *dev, w, seed);
+  ElFluctuationKernel<<<grid, kThreadsPerBlock, 0, st>>>(h->view, *dev, w, seed);
+  ElDiscreteKernel<<<grid, kThreadsPerBlock, 0, st>>>(h->view, *dev, w, seed);
+  ElSamplerKernel<kQMoller><<<grid, kThreadsPerBlock, 0, st>>>(h->view, *dev, w, *sec, seed);
+  ElSamplerKernel<kQBhabha><<<grid, kThreadsPerBlock, 0, st>>>(h->view, *dev, w, *sec, seed);
+  ElSamplerKernel<kQSB><<<grid, kThreadsPerBlock, 0, st>>>(h->view, *dev, w, *sec, seed);
+  ElSamplerKernel<kQRB><<<grid, kThreadsPerBlock, 0, st>>>(h->view, *dev, w, *sec, seed);
+  ElSamplerKernel<kQAnnih><<<grid, kThreadsPerBlock, 0, st>>>(h->view, *dev, w, *sec, seed);
+  ElSamplerKernel<kQAtRest><<<grid, kThreadsPerBlock, 0, st>>>(h->view, *dev, w, *sec, seed);
+  h->launches += 9;
+  G4H_CUDA(cudaGetLastError());
+  return 0;
+}
+
 }  // namespace
 
 extern "C" {
@@ -309,6 +373,10 @@ int g4hb200_create(const G4HB200Tables* tables, int device, G4HB200** out) {
     }
   }
   h->view = MakeView(d);
+  {
+    const char* mono = std::getenv("G4HB200_MONOLITH");
+    h->monolith = mono != nullptr && mono[0] == '1';
+  }
   G4H_CUDA(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
   std::memset(&h->elDev, 0, sizeof(h->elDev));
   std::memset(&h->gmDev, 0, sizeof(h->gmDev));
@@ -323,6 +391,7 @@ int g4hb200_destroy(G4HB200* h) {
   if (h->elCap > 0) g4hb200_electron_batch_free(h, &h->elDev);
   if (h->gmCap > 0) g4hb200_gamma_batch_free(h, &h->gmDev);
   if (h->secCap > 0) g4hb200_secondary_queue_free(h, &h->secDev);
+  if (h->elWorkMem != nullptr) cudaFree(h->elWorkMem);
   if (h->stream != nullptr) cudaStreamDestroy(h->stream);
   if (h->arena != nullptr) cudaFree(h->arena);
   delete h;
@@ -565,10 +634,12 @@ int g4hb200_electron_howfar(G4HB200* h, G4HB200ElectronBatch* dev, uint64_t seed
   return LaunchElectron<0>(h, dev, nullptr, seed, stream);
 }
 int g4hb200_electron_perform(G4HB200* h, G4HB200ElectronBatch* dev, G4HB200SecondaryQueue* sec, uint64_t seed, void* stream) {
-  return LaunchElectron<1>(h, dev, sec, seed, stream);
+  if (h != nullptr && h->monolith) return LaunchElectron<1>(h, dev, sec, seed, stream);
+  return LaunchElectronPipeline<false>(h, dev, sec, seed, stream);
 }
 int g4hb200_electron_step(G4HB200* h, G4HB200ElectronBatch* dev, G4HB200SecondaryQueue* sec, uint64_t seed, void* stream) {
-  return LaunchElectron<2>(h, dev, sec, seed, stream);
+  if (h != nullptr && h->monolith) return LaunchElectron<2>(h, dev, sec, seed, stream);
+  return LaunchElectronPipeline<true>(h, dev, sec, seed, stream);
 }
 int g4hb200_gamma_howfar(G4HB200* h, G4HB200GammaBatch* dev, uint64_t seed, void* stream) {
   return LaunchGamma<0>(h, dev, nullptr, seed, stream);
@@ -601,7 +672,7 @@ int g4hb200_electron_step_host(G4HB200* h, G4HB200ElectronBatch* host, G4HB200Se
   // H2D: the 7 persistent groups + meta (128 B / track)
   if ((rc = CopyElectron(host, &h->elDev, cudaMemcpyHostToDevice, st, 0, 7, true, false)) != 0) return rc;
   if ((rc = g4hb200_secondary_queue_reset(h, &h->secDev, st)) != 0) return rc;
-  if ((rc = LaunchElectron<2>(h, &h->elDev, &h->secDev, seed, st)) != 0) return rc;
+  if ((rc = g4hb200_electron_step(h, &h->elDev, &h->secDev, seed, st)) != 0) return rc;
   // D2H: persistent + result groups + meta + winner (180 B / track) and the secondaries
   if ((rc = CopyElectron(&h->elDev, host, cudaMemcpyDeviceToHost, st, 0, 10, true, true)) != 0) return rc;
   if ((rc = g4hb200_secondary_queue_download(h, &h->secDev, hostSec, st)) != 0) return rc;

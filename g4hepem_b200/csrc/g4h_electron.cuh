@@ -586,38 +586,54 @@ G4H_FN double SampleEnergyLossFluctuation(double tcut, double excEner, double me
   return eloss * scaling;
 }
 
-// SampleLossFluctuations (.icc:324-368)
-G4H_FN bool SampleLossFluctuations(const TablesView& tv, ElectronState& s, Rng& rng) {
-  const double pStepLength = s.pStep;
-  (void)pStepLength;
-  const bool isElectron = !s.isPositron;
-  const int theIMC      = s.imc;
-  const double thePreStepEkin = s.preStepEkin;
-  double finalEkin = s.ekin;
-  double eloss     = s.edep;
-  const int iregion = G4H_LD(tv.mcIreg + theIMC);
+// SampleLossFluctuations (.icc:324-368) in three pieces, so that the pipelined Perform can run the sampling
+// itself as its own kernel over the tracks that need it:
+//   LossFluctuationIsSampled  the condition of .icc:337
+//   LossFluctuationSample     .icc:338-350: the fluctuated loss and the energy after it
+//   LossFluctuationFinish     .icc:352-367: tracking cut, final energy and deposit
+G4H_FN bool LossFluctuationIsSampled(const TablesView& tv, const ElectronState& s) {
+  const int iregion = G4H_LD(tv.mcIreg + s.imc);
   const bool isFluctuation = G4H_LD(tv.regionPars + 8 * iregion + kRIsFluct) != 0.0;
   const double kFluctParMinEnergy = 1.E-5;
-  if (isFluctuation && eloss > kFluctParMinEnergy) {
-    const double elCut   = G4H_LD(tv.mcCuts + 4 * theIMC + kCElCut);
-    const int theImat    = G4H_LD(tv.mcImat + theIMC);
-    const double meanExE = G4H_LD(tv.matPars + 16 * theImat + kMMeanExE);
-    const double tmax = isElectron ? 0.5 * thePreStepEkin : thePreStepEkin;
-    const double tcut = Min(elCut, tmax);
-    eloss = SampleEnergyLossFluctuation(tcut, meanExE, eloss, rng);
-    eloss = Max(eloss, 0.0);
-    finalEkin = thePreStepEkin - eloss;
-  }
+  return isFluctuation && s.edep > kFluctParMinEnergy;
+}
+
+G4H_FN void LossFluctuationSample(const TablesView& tv, int imc, bool isElectron, double thePreStepEkin, double meanLoss,
+                                  Rng& rng, double& finalEkin, double& eloss) {
+  const double elCut   = G4H_LD(tv.mcCuts + 4 * imc + kCElCut);
+  const int theImat    = G4H_LD(tv.mcImat + imc);
+  const double meanExE = G4H_LD(tv.matPars + 16 * theImat + kMMeanExE);
+  const double tmax = isElectron ? 0.5 * thePreStepEkin : thePreStepEkin;
+  const double tcut = Min(elCut, tmax);
+  eloss = SampleEnergyLossFluctuation(tcut, meanExE, meanLoss, rng);
+  eloss = Max(eloss, 0.0);
+  finalEkin = thePreStepEkin - eloss;
+}
+
+// returns true if the track was stopped; sets {ekin, logEkin = not cached} and edep
+G4H_FN bool LossFluctuationFinish(const TablesView& tv, double thePreStepEkin, double finalEkin, double eloss, double& ekinOut,
+                                  double& edepOut) {
   if (finalEkin <= tv.elTrackingCut) {
-    eloss     = thePreStepEkin;
-    finalEkin = 0.0;
-    SetEKin(s, finalEkin);
-    s.edep = eloss;
+    ekinOut = 0.0;
+    edepOut = thePreStepEkin;
     return true;
   }
-  SetEKin(s, finalEkin);
-  s.edep = eloss;
+  ekinOut = finalEkin;
+  edepOut = eloss;
   return false;
+}
+
+G4H_FN bool SampleLossFluctuations(const TablesView& tv, ElectronState& s, Rng& rng) {
+  double finalEkin = s.ekin;
+  double eloss     = s.edep;
+  if (LossFluctuationIsSampled(tv, s)) {
+    LossFluctuationSample(tv, s.imc, !s.isPositron, s.preStepEkin, eloss, rng, finalEkin, eloss);
+  }
+  double ekin, edep;
+  const bool stopped = LossFluctuationFinish(tv, s.preStepEkin, finalEkin, eloss, ekin, edep);
+  SetEKin(s, ekin);
+  s.edep = edep;
+  return stopped;
 }
 
 // PerformContinuous (.icc:375-405)
@@ -642,8 +658,8 @@ G4H_FN bool PerformContinuous(const TablesView& tv, ElectronState& s, Rng& rng) 
   return SampleLossFluctuations(tv, s, rng);
 }
 
-// CheckDelta (.icc:408-423)
-G4H_FN bool CheckDelta(const TablesView& tv, ElectronState& s, double rand) {
+// CheckDelta (.icc:408-423); mfpWon is fMFPs[fPIndxWon]
+G4H_FN bool CheckDeltaWith(const TablesView& tv, ElectronState& s, double mfpWon, double rand) {
   const bool isElectron = !s.isPositron;
   const ElectronTablesView& ed = tv.el[isElectron ? 0 : 1];
   const int iDProc      = s.winner;
@@ -655,7 +671,13 @@ G4H_FN bool CheckDelta(const TablesView& tv, ElectronState& s, double rand) {
       (iDProc < 2 ? RestMacXSec(ed, theIMC, theEkin, theLEkin, iDProc == 0)
                   : (iDProc < 3 ? MacXSecAnnihilation(theEkin, G4H_LD(tv.matPars + 16 * theMatIndex + kMElectronDensity))
                                 : MacXSecNuclear(ed, theMatIndex, theEkin, theLEkin)));
-  return mxsec <= 0.0 || rand > mxsec * s.mfp[iDProc];
+  return mxsec <= 0.0 || rand > mxsec * mfpWon;
+}
+
+G4H_FN bool CheckDelta(const TablesView& tv, ElectronState& s, double rand) {
+  const int w = s.winner;
+  const double mfpWon = w == 0 ? s.mfp[0] : w == 1 ? s.mfp[1] : w == 2 ? s.mfp[2] : s.mfp[3];
+  return CheckDeltaWith(tv, s, mfpWon, rand);
 }
 
 }  // namespace g4h

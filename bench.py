@@ -41,6 +41,19 @@ UNIT = "track-steps/s"
 READ_BYTES = 7 * 16 + 16           # 7 persistent pair groups + meta
 WRITE_BYTES = 10 * 16 + 16 + 4     # persistent + 3 result groups + meta + winner
 SEC_BYTES = 16 + 16 + 8 + 8        # one secondary record
+# algorithmic bytes per track of every pipeline stage: (read, written, secondaries appended); DESIGN.md par. 4
+STAGE_BYTES = {
+    "ElectronKernel<0> (HowFar)": (7 * 16 + 16, 10 * 16 + 16 + 4 + 6 * 16, 0),
+    "ElContinuousKernel": (7 * 16 + 16 + 9 * 16 + 4, 10 * 16 + 16 + 4 + 16 + 16, 0),
+    "ElFluctuationKernel": (4 + 16 + 3 * 16 + 4, 3 * 16 + 16, 0),
+    "ElDiscreteKernel": (4 + 16 + 16 + 4 + 16 + 16, 3 * 16, 0),
+    "ElSamplerKernel<Moller>": (4 + 16 + 3 * 16, 3 * 16 + 16, 1),
+    "ElSamplerKernel<Bhabha>": (4 + 16 + 3 * 16, 3 * 16 + 16, 1),
+    "ElSamplerKernel<SeltzerBerger>": (4 + 16 + 3 * 16, 3 * 16 + 16, 1),
+    "ElSamplerKernel<RelBrem>": (4 + 16 + 3 * 16, 3 * 16 + 16, 1),
+    "ElSamplerKernel<Annihilation>": (4 + 16 + 3 * 16, 3 * 16 + 16, 2),
+    "ElSamplerKernel<AtRest>": (4 + 16, 16, 2),
+}
 
 
 def _workload_config(n_tracks, ring):
@@ -240,6 +253,21 @@ def run_gpu(args):
     kernel_ms = float(np.mean([a.elapsed_time(b) for a, b in kev]))
     n_sec = int(sec.count[0].item())
     launches = engine.launch_count - launches0
+    # per-kernel durations: the same steps again over re-initialised ring batches, this time with CUDA events
+    # around every kernel of the pipeline (on the launch stream).  Kept out of the region `value` is timed over:
+    # an event between two small kernels opens a ~10 us gap that back-to-back launches do not have.
+    t_steps = min(steps, ring_n, 10)
+    for i in range(t_steps):
+        ring[i].upload(pristine, groups=batches.ElectronHostBatch.PAIR_GROUPS + ("meta",))
+    torch.cuda.synchronize()
+    engine.set_kernel_timing(True)
+    engine.kernel_times()
+    for i in range(t_steps):
+        sec.reset()
+        eng.ElectronManager.Step(engine, ring[i], sec, SEED)
+    torch.cuda.synchronize()
+    stage_times = engine.kernel_times()
+    engine.set_kernel_timing(False)
     clocks = sampler.stop() if sampler is not None else None
     if dist is not None:
         t = torch.tensor([elapsed_ms], dtype=torch.float64, device="cuda")
@@ -247,11 +275,14 @@ def run_gpu(args):
         elapsed_ms = float(t.item())
     value = world * n * steps / (elapsed_ms * 1e-3)
 
-    # ---- the one collective of the path: sum of deposited energy over all ranks (cf. Run::Merge) --------------
-    edep = ring[(warmup + steps - 1) % ring_n].t["edep_dispx"][:n, 0].sum().reshape(1)
-    if dist is not None:
-        dist.all_reduce(edep)
-    edep_sum = float(edep.item())
+    # ---- the one collective of the path: per-couple sums of the deposited energy over all ranks (cf. Run::Merge) ----
+    from g4hepem_b200 import sharding
+
+    last = ring[(warmup + steps - 1) % ring_n]
+    hist = torch.zeros(ft.num_matcut, dtype=torch.float64, device="cuda")
+    hist.index_add_(0, last.t["meta"][:n, 0].long(), last.t["edep_dispx"][:n, 0])
+    tot, _ = sharding.allreduce_scores(hist.cpu().numpy(), [n], dist, device=torch.device("cuda", local))
+    edep_sum = float(tot.sum())
 
     # ---- e2e: host buffers through the C-ABI ---------------------------------------------------------------
     e2e_steps = min(steps, args.e2e_steps)
@@ -288,8 +319,18 @@ def run_gpu(args):
         return 0
 
     peak, peak_src = _peaks()
-    alg_bytes = n * (READ_BYTES + WRITE_BYTES) + n_sec * SEC_BYTES
-    achieved = alg_bytes / (kernel_ms * 1e-3) / 1e9
+    step_bytes = n * (READ_BYTES + WRITE_BYTES) + n_sec * SEC_BYTES
+    stages = []
+    for name, (ms_sum, nl, items) in stage_times.items():
+        if nl == 0:
+            continue
+        rd, wr, nsec = STAGE_BYTES[name]
+        per_launch_bytes = (items / nl) * (rd + wr + nsec * SEC_BYTES)
+        ms = ms_sum / nl
+        stages.append({"kernel": name, "ms": ms, "tracks": items / nl, "bytes": per_launch_bytes,
+                       "gbs": per_launch_bytes / (ms * 1e-3) / 1e9 if ms > 0 else None})
+    dom = max(stages, key=lambda x: x["ms"])
+    achieved = dom["gbs"]
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": warmup,
         "ms_per_step": elapsed_ms / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -299,9 +340,14 @@ def run_gpu(args):
         "gpu_launches": int(launches),
         "clocks": clocks,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": _traffic_from_profile(), "kernel": "g4h::ElectronKernel<2>", "kernel_ms": kernel_ms,
-                     "algorithmic_bytes_per_launch": alg_bytes, "peak_source": peak_src,
-                     "secondaries_per_launch": n_sec},
+                     "traffic": _traffic_from_profile(dom["kernel"]), "kernel": dom["kernel"], "kernel_ms": dom["ms"],
+                     "algorithmic_bytes_per_launch": dom["bytes"], "peak_source": peak_src,
+                     "kernel_share_of_step": dom["ms"] / sum(x["ms"] for x in stages),
+                     "whole_step": {"algorithmic_bytes": step_bytes, "ms": kernel_ms,
+                                    "gbs": step_bytes / (kernel_ms * 1e-3) / 1e9,
+                                    "frac": step_bytes / (kernel_ms * 1e-3) / 1e9 / peak,
+                                    "secondaries": n_sec},
+                     "stages": stages},
         "edep_sum_mev_last_step_allreduced": edep_sum,
     }
     if not args.no_cpu_baseline and world == 1:
@@ -319,13 +365,13 @@ def run_gpu(args):
     return 0
 
 
-def _traffic_from_profile():
-    """dram bytes read+written per launch of the step kernel from the committed `ncu --set full` summary."""
-    path = os.path.join(ROOT, "profiles", "r01_electron_step_full.json")
+def _traffic_from_profile(kernel):
+    """dram bytes read+written per launch of `kernel` from the committed `ncu --set full` summary."""
+    path = os.path.join(ROOT, "profiles", "r01_pipeline_full.json")
     if os.path.exists(path):
         try:
             with open(path) as f:
-                return json.load(f).get("dram_bytes_per_launch")
+                return json.load(f).get(kernel, {}).get("dram_bytes_per_launch")
         except (OSError, ValueError):
             return None
     return None

@@ -6,7 +6,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "libg4hepem_b200.so")
+# G4HB200_LIB: an alternative build of the same library (kernel tuning A/B runs)
+LIB_PATH = os.environ.get("G4HB200_LIB") or os.path.join(_HERE, "csrc", "libg4hepem_b200.so")
 
 c_dp = C.POINTER(C.c_double)
 c_ip = C.POINTER(C.c_int32)
@@ -154,6 +155,7 @@ F_MSC_NO_SCATTER = 0x20
 F_GAUSS_CACHED = 0x40
 
 SEC_ELECTRON, SEC_POSITRON, SEC_GAMMA = 0, 1, 2
+NUM_STAGES = 10
 
 # every symbol include/g4hepem_b200.h declares: name -> (restype, argtypes)
 _vp = C.c_void_p
@@ -191,6 +193,9 @@ PROTOTYPES = {
     "g4hb200_electron_step_host": (C.c_int, [_H, C.POINTER(ElectronBatch), C.POINTER(SecondaryQueue), C.c_uint64]),
     "g4hb200_gamma_step_host": (C.c_int, [_H, C.POINTER(GammaBatch), C.POINTER(SecondaryQueue), C.c_uint64]),
     "g4hb200_launch_count": (C.c_int64, [_H]),
+    "g4hb200_set_kernel_timing": (C.c_int, [_H, C.c_int]),
+    "g4hb200_kernel_times": (C.c_int, [_H, _vp, _vp, _vp]),
+    "g4hb200_stage_name": (C.c_char_p, [C.c_int]),
 }
 
 _lib = None

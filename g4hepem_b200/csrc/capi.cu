@@ -106,6 +106,15 @@ struct G4HB200 {
   void* elWorkMem = nullptr;
   int64_t elWorkCap = 0;
   bool monolith = false;  // G4HB200_MONOLITH=1: the one-kernel-per-step variant (kept for A/B measurements)
+  // per-kernel timing (g4hb200_set_kernel_timing): one event row per timed pipeline call
+  bool timing = false;
+  struct TimedCall {
+    cudaEvent_t ev[G4HB200_NUM_STAGES + 1];
+    bool ran[G4HB200_NUM_STAGES];
+    int32_t* counts;  // pinned copy of the queue counters of that call
+    int64_t n;
+  };
+  std::vector<TimedCall> timed;
 };
 
 namespace {
@@ -264,23 +273,61 @@ int LaunchElectronPipeline(G4HB200* h, G4HB200ElectronBatch* dev, G4HB200Seconda
   const int grid = GridFor(dev->n, h->smCount, 8);
   const ElectronWork& w = h->elWork;
   G4H_CUDA(cudaMemsetAsync(w.count, 0, kNumElQueues * sizeof(int32_t), st));
-  if (kFused) {
-    ElectronKernel<0><<<grid, kThreadsPerBlock, 0, st>>>(h->view, *dev, NullQueue(), seed);
-    ++h->launches;
+  G4HB200::TimedCall* tc = nullptr;
+  if (h->timing) {
+    h->timed.emplace_back();
+    tc = &h->timed.back();
+    tc->n = dev->n;
+    tc->counts = nullptr;
+    for (auto& e : tc->ev) G4H_CUDA(cudaEventCreate(&e));
+    for (auto& r : tc->ran) r = false;
+    G4H_CUDA(cudaMallocHost(reinterpret_cast<void**>(&tc->counts), kNumElQueues * sizeof(int32_t)));
+    G4H_CUDA(cudaEventRecord(tc->ev[0], st));
   }
+  int stage = 0;
+  auto done = [&](bool ran) -> cudaError_t {
+    if (ran) ++h->launches;
+    if (tc != nullptr) {
+      tc->ran[stage] = ran;
+      const cudaError_t e = cudaEventRecord(tc->ev[stage + 1], st);
+      if (e != cudaSuccess) return e;
+    }
+    ++stage;
+    return cudaSuccess;
+  };
+  if (kFused) ElectronKernel<0><<<grid, kThreadsPerBlock, 0, st>>>(h->view, *dev, NullQueue(), seed);
+  G4H_CUDA(done(kFused));
   ElContinuousKernel<<<grid, kThreadsPerBlock, 0, st>>>(h->view, *dev, w, seed);
+  G4H_CUDA(done(true));
   ElFluctuationKernel<<<grid, kThreadsPerBlock, 0, st>>>(h->view, *dev, w, seed);
+  G4H_CUDA(done(true));
   ElDiscreteKernel<<<grid, kThreadsPerBlock, 0, st>>>(h->view, *dev, w, seed);
+  G4H_CUDA(done(true));
   ElSamplerKernel<kQMoller><<<grid, kThreadsPerBlock, 0, st>>>(h->view, *dev, w, *sec, seed);
+  G4H_CUDA(done(true));
   ElSamplerKernel<kQBhabha><<<grid, kThreadsPerBlock, 0, st>>>(h->view, *dev, w, *sec, seed);
+  G4H_CUDA(done(true));
   ElSamplerKernel<kQSB><<<grid, kThreadsPerBlock, 0, st>>>(h->view, *dev, w, *sec, seed);
+  G4H_CUDA(done(true));
   ElSamplerKernel<kQRB><<<grid, kThreadsPerBlock, 0, st>>>(h->view, *dev, w, *sec, seed);
+  G4H_CUDA(done(true));
   ElSamplerKernel<kQAnnih><<<grid, kThreadsPerBlock, 0, st>>>(h->view, *dev, w, *sec, seed);
+  G4H_CUDA(done(true));
   ElSamplerKernel<kQAtRest><<<grid, kThreadsPerBlock, 0, st>>>(h->view, *dev, w, *sec, seed);
-  h->launches += 9;
+  G4H_CUDA(done(true));
+  if (tc != nullptr) {
+    G4H_CUDA(cudaMemcpyAsync(tc->counts, w.count, kNumElQueues * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+  }
   G4H_CUDA(cudaGetLastError());
   return 0;
 }
+
+// pipeline stage -> queue that feeds it (-1: every track of the batch)
+const int kStageQueue[G4HB200_NUM_STAGES] = {-1, -1, kQFluct, kQDiscrete, kQMoller, kQBhabha, kQSB, kQRB, kQAnnih, kQAtRest};
+const char* const kStageName[G4HB200_NUM_STAGES] = {
+    "ElectronKernel<0> (HowFar)", "ElContinuousKernel", "ElFluctuationKernel", "ElDiscreteKernel", "ElSamplerKernel<Moller>",
+    "ElSamplerKernel<Bhabha>", "ElSamplerKernel<SeltzerBerger>", "ElSamplerKernel<RelBrem>", "ElSamplerKernel<Annihilation>",
+    "ElSamplerKernel<AtRest>"};
 
 }  // namespace
 
@@ -708,5 +755,40 @@ int g4hb200_gamma_step_host(G4HB200* h, G4HB200GammaBatch* host, G4HB200Secondar
 }
 
 int64_t g4hb200_launch_count(const G4HB200* h) { return h != nullptr ? h->launches : 0; }
+
+const char* g4hb200_stage_name(int k) { return (k >= 0 && k < G4HB200_NUM_STAGES) ? kStageName[k] : ""; }
+
+int g4hb200_set_kernel_timing(G4HB200* h, int enable) {
+  int rc = CheckHandle(h);
+  if (rc != 0) return rc;
+  h->timing = enable != 0;
+  return 0;
+}
+
+int g4hb200_kernel_times(G4HB200* h, double* ms_sum, int64_t* launches, int64_t* items) {
+  int rc = CheckHandle(h);
+  if (rc != 0) return rc;
+  if (ms_sum == nullptr || launches == nullptr || items == nullptr) return Fail(G4HB200_EINVAL, "null argument");
+  for (int k = 0; k < G4HB200_NUM_STAGES; ++k) {
+    ms_sum[k] = 0.0;
+    launches[k] = 0;
+    items[k] = 0;
+  }
+  for (auto& tc : h->timed) {
+    G4H_CUDA(cudaEventSynchronize(tc.ev[G4HB200_NUM_STAGES]));
+    for (int k = 0; k < G4HB200_NUM_STAGES; ++k) {
+      if (!tc.ran[k]) continue;
+      float ms = 0.f;
+      G4H_CUDA(cudaEventElapsedTime(&ms, tc.ev[k], tc.ev[k + 1]));
+      ms_sum[k] += ms;
+      launches[k] += 1;
+      items[k] += kStageQueue[k] < 0 ? tc.n : tc.counts[kStageQueue[k]];
+    }
+    for (auto& e : tc.ev) cudaEventDestroy(e);
+    cudaFreeHost(tc.counts);
+  }
+  h->timed.clear();
+  return 0;
+}
 
 }  // extern "C"

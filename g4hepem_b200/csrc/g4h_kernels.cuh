@@ -14,6 +14,17 @@
 namespace g4h {
 
 constexpr int kThreadsPerBlock = 256;
+// resident CTAs per SM the big kernels are compiled for (register cap = 65536 / (256 * k)); tuned on the B200,
+// see profiles/
+#ifndef G4H_MINB_HOWFAR
+#define G4H_MINB_HOWFAR 2
+#endif
+#ifndef G4H_MINB_CONT
+#define G4H_MINB_CONT 2
+#endif
+#ifndef G4H_MINB_QUEUE
+#define G4H_MINB_QUEUE 2
+#endif
 
 // ---- warp aggregated append to the secondary queue -------------------------------------------------------
 // called by all 32 lanes of a warp (sec.n may be 0): ballots give each lane its offset, one atomicAdd per
@@ -45,7 +56,7 @@ __device__ __forceinline__ void AppendSecondaries(const G4HB200SecondaryQueue& q
 // ---- e-/e+ ---------------------------------------------------------------------------------------------------
 // mode 0: HowFar, 1: Perform, 2: fused HowFar + Perform
 template <int kMode>
-__global__ void __launch_bounds__(kThreadsPerBlock)
+__global__ void __launch_bounds__(kThreadsPerBlock, kMode == 0 ? G4H_MINB_HOWFAR : 1)
 ElectronKernel(const __grid_constant__ TablesView tv, const __grid_constant__ G4HB200ElectronBatch b,
                const __grid_constant__ G4HB200SecondaryQueue q, uint64_t seed) {
   const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;

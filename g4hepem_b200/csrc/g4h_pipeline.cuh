@@ -44,7 +44,7 @@ __device__ __forceinline__ void QueuePush(int32_t* __restrict__ q, int32_t* __re
 }
 
 // ---- continuous part for every track --------------------------------------------------------------------------
-__global__ void __launch_bounds__(kThreadsPerBlock, 2)
+__global__ void __launch_bounds__(kThreadsPerBlock, G4H_MINB_CONT)
 ElContinuousKernel(const __grid_constant__ TablesView tv, const __grid_constant__ G4HB200ElectronBatch b,
                    const __grid_constant__ ElectronWork w, uint64_t seed) {
   const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
@@ -102,7 +102,7 @@ ElContinuousKernel(const __grid_constant__ TablesView tv, const __grid_constant_
 }
 
 // ---- energy loss fluctuation over its queue ---------------------------------------------------------------------
-__global__ void __launch_bounds__(kThreadsPerBlock)
+__global__ void __launch_bounds__(kThreadsPerBlock, G4H_MINB_QUEUE)
 ElFluctuationKernel(const __grid_constant__ TablesView tv, const __grid_constant__ G4HB200ElectronBatch b,
                     const __grid_constant__ ElectronWork w, uint64_t seed) {
   const int cnt = w.count[kQFluct];
@@ -142,7 +142,7 @@ ElFluctuationKernel(const __grid_constant__ TablesView tv, const __grid_constant
 }
 
 // ---- head of PerformDiscrete: real or delta interaction, which model -----------------------------------------------
-__global__ void __launch_bounds__(kThreadsPerBlock)
+__global__ void __launch_bounds__(kThreadsPerBlock, G4H_MINB_QUEUE)
 ElDiscreteKernel(const __grid_constant__ TablesView tv, const __grid_constant__ G4HB200ElectronBatch b,
                  const __grid_constant__ ElectronWork w, uint64_t seed) {
   const int cnt = w.count[kQDiscrete];
@@ -196,7 +196,7 @@ ElDiscreteKernel(const __grid_constant__ TablesView tv, const __grid_constant__ 
 
 // ---- final state samplers, one kernel per model -----------------------------------------------------------------------
 template <int kQueue>
-__global__ void __launch_bounds__(kThreadsPerBlock)
+__global__ void __launch_bounds__(kThreadsPerBlock, G4H_MINB_QUEUE)
 ElSamplerKernel(const __grid_constant__ TablesView tv, const __grid_constant__ G4HB200ElectronBatch b,
                 const __grid_constant__ ElectronWork w, const __grid_constant__ G4HB200SecondaryQueue sq, uint64_t seed) {
   const int cnt = w.count[kQueue];

@@ -60,6 +60,17 @@ class Engine:
     def launch_count(self):
         return int(self.lib.g4hb200_launch_count(self.handle))
 
+    def set_kernel_timing(self, enable=True):
+        _capi.check(self.lib.g4hb200_set_kernel_timing(self.handle, int(enable)), "set_kernel_timing")
+
+    def kernel_times(self):
+        """Per pipeline stage since the last call: {name: (ms_sum, launches, items)}."""
+        ms = np.zeros(_capi.NUM_STAGES)
+        ln = np.zeros(_capi.NUM_STAGES, dtype=np.int64)
+        it = np.zeros(_capi.NUM_STAGES, dtype=np.int64)
+        _capi.check(self.lib.g4hb200_kernel_times(self.handle, ms.ctypes.data, ln.ctypes.data, it.ctypes.data), "kernel_times")
+        return {self.lib.g4hb200_stage_name(k).decode(): (float(ms[k]), int(ln[k]), int(it[k])) for k in range(_capi.NUM_STAGES)}
+
     # ---- look-ups on torch CUDA tensors ------------------------------------------------------------------
     def electron_lookups(self, imc, ekin, logekin, is_electron=True):
         torch = _torch()

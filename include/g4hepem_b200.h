@@ -273,6 +273,17 @@ int g4hb200_gamma_step_host(G4HB200* h, G4HB200GammaBatch* host, G4HB200Secondar
 /* number of kernels launched through this handle so far (for the bench's gpu_launches) */
 int64_t g4hb200_launch_count(const G4HB200* h);
 
+/* ---- per-kernel device timing of the e-/e+ step pipeline -------------------------------------------
+ * With timing enabled every pipelined g4hb200_electron_step / _perform call records CUDA events on its
+ * stream around each of its kernels.  g4hb200_kernel_times synchronises those events and returns, per
+ * pipeline stage k < G4HB200_NUM_STAGES, the summed device time in ms (ms_sum[k]), the number of launches
+ * (launches[k]) and the summed number of tracks the stage processed (items[k], from the queue counters);
+ * the sums restart at every call.  Stage names: g4hb200_stage_name(k). */
+#define G4HB200_NUM_STAGES 10
+int g4hb200_set_kernel_timing(G4HB200* h, int enable);
+int g4hb200_kernel_times(G4HB200* h, double* ms_sum, int64_t* launches, int64_t* items);
+const char* g4hb200_stage_name(int k);
+
 #ifdef __cplusplus
 }
 #endif

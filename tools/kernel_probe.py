@@ -33,6 +33,18 @@ def timed(name, fn, prep):
 
 
 host = batches.make_electron_batch(n, ft.num_matcut, seed=SEED)
+if os.environ.get("PROBE_SORT"):
+    # what a (couple, charge, energy)-sorted queue would give the kernels
+    mode = os.environ["PROBE_SORT"]
+    ebin = np.floor(np.log(host.ekin_logekin[:, 0]) * float(os.environ.get("PROBE_EBINS", "4"))).astype(np.int64)
+    pos = (host.meta[:, 1] & 1).astype(np.int64)
+    imc = host.meta[:, 0].astype(np.int64)
+    key = {"full": (imc * 2 + pos) * 4096 + (ebin + 2048), "energy": ebin, "couple": imc * 2 + pos,
+           "exact": None}[mode]
+    order = np.argsort(host.ekin_logekin[:, 0] + 1e9 * (imc * 2 + pos), kind="stable") if key is None else np.argsort(key, kind="stable")
+    for g in host.groups() + ("meta", "winner"):
+        getattr(host, g)[...] = getattr(host, g)[order]
+    print("sorted by", mode, flush=True)
 dev = eng.ElectronDeviceBatch(n)
 sec = eng.SecondaryDeviceQueue(2 * n)
 

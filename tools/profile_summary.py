@@ -1,0 +1,58 @@
+#!/usr/bin/env python
+"""Summarise an `ncu --set full` report of the pipelined e-/e+ step into profiles/<tag>.json and .md.
+usage: tools/profile_summary.py <report.ncu-rep> <tag> "<command the report was captured with>" """
+import csv
+import io
+import json
+import os
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+rep, tag, cmd = sys.argv[1], sys.argv[2], sys.argv[3]
+raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+rows = list(csv.reader(io.StringIO(raw)))
+hdr, units = rows[0], rows[1]
+NAMES = [("ElectronKernel<0>", "ElectronKernel<0> (HowFar)"), ("ElContinuousKernel", "ElContinuousKernel"),
+         ("ElFluctuationKernel", "ElFluctuationKernel"), ("ElDiscreteKernel", "ElDiscreteKernel"),
+         ("ElSamplerKernel<3>", "ElSamplerKernel<Moller>"), ("ElSamplerKernel<4>", "ElSamplerKernel<Bhabha>"),
+         ("ElSamplerKernel<5>", "ElSamplerKernel<SeltzerBerger>"), ("ElSamplerKernel<6>", "ElSamplerKernel<RelBrem>"),
+         ("ElSamplerKernel<7>", "ElSamplerKernel<Annihilation>"), ("ElSamplerKernel<2>", "ElSamplerKernel<AtRest>"),
+         ("ElectronKernel<2>", "ElectronKernel<2> (monolithic step)"), ("GammaKernel<2>", "GammaKernel<2> (monolithic step)"),
+         ("GammaKernel<0>", "GammaKernel<0> (HowFar)")]
+SCALE = {'Mbyte': 1e6, 'Kbyte': 1e3, 'byte': 1, 'Gbyte': 1e9, 'us': 1e-3, 'ms': 1, 'ns': 1e-6, 'msecond': 1, 'usecond': 1e-3, 'nsecond': 1e-6}
+
+
+def col(r, k):
+    return float(r[hdr.index(k)].replace(',', '')) * SCALE.get(units[hdr.index(k)], 1)
+
+
+out = {}
+md = [f"# {tag} -- `ncu --set full` summary", "", f"Command (on the B200 box): `{cmd}`.",
+      "Times under ncu are cold-cache and serialised; compare shares, not absolutes.", "",
+      "| kernel | ms | dram MB (rd+wr) | regs | lanes/32 | issue % | fp64 pipe % | L2 hit % | warp-inst (M) | stall no-instr | stall long-sb | stall wait |",
+      "|---|---|---|---|---|---|---|---|---|---|---|---|"]
+for r in rows[2:]:
+    kn = r[hdr.index('Kernel Name')]
+    key = next((b for a, b in NAMES if a in kn), None)
+    if key is None or key in out:
+        continue
+    d = dict(ms=col(r, 'gpu__time_duration.sum'),
+             dram_bytes_per_launch=col(r, 'dram__bytes_read.sum') + col(r, 'dram__bytes_write.sum'),
+             dram_read=col(r, 'dram__bytes_read.sum'), dram_write=col(r, 'dram__bytes_write.sum'),
+             registers=col(r, 'launch__registers_per_thread'),
+             lanes=col(r, 'smsp__thread_inst_executed_per_inst_executed.ratio'),
+             issue_active_pct=col(r, 'smsp__issue_active.avg.pct_of_peak_sustained_active'),
+             fp64_pipe_pct=col(r, 'sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active'),
+             l2_hit_pct=col(r, 'lts__t_sector_hit_rate.pct'), warp_inst=col(r, 'smsp__inst_executed.sum'),
+             stall_no_instruction=col(r, 'smsp__average_warps_issue_stalled_no_instruction_per_issue_active.ratio'),
+             stall_long_scoreboard=col(r, 'smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio'),
+             stall_wait=col(r, 'smsp__average_warps_issue_stalled_wait_per_issue_active.ratio'))
+    out[key] = d
+    md.append("| %s | %.3f | %.1f | %d | %.1f | %.1f | %.1f | %.1f | %.1f | %.2f | %.2f | %.2f |" % (
+        key, d['ms'], d['dram_bytes_per_launch'] / 1e6, d['registers'], d['lanes'], d['issue_active_pct'], d['fp64_pipe_pct'],
+        d['l2_hit_pct'], d['warp_inst'] / 1e6, d['stall_no_instruction'], d['stall_long_scoreboard'], d['stall_wait']))
+os.makedirs(os.path.join(ROOT, "profiles"), exist_ok=True)
+json.dump(out, open(os.path.join(ROOT, "profiles", tag + ".json"), "w"), indent=1)
+open(os.path.join(ROOT, "profiles", tag + ".md"), "w").write("\n".join(md) + "\n")
+print("\n".join(md))

@@ -76,8 +76,9 @@ G4H_FN void LoadElectron(const G4HB200ElectronBatch& b, int64_t i, uint64_t seed
   s.mscDisplace  = (f & G4HB200_F_MSC_DISPLACE) != 0u;
   s.mscNoScatter = (f & G4HB200_F_MSC_NO_SCATTER) != 0u;
   rng.Init(seed, static_cast<uint32_t>(m.id), static_cast<uint32_t>(m.draw), (f & G4HB200_F_GAUSS_CACHED) != 0u, tg.b);
-  // defaults of the fields HowFar defines (G4HepEmTrack::ReSet / G4HepEmMSCTrackData::ReSet values)
-  s.winner = -1; s.gStep = 0.0; s.pStep = 0.0; s.edep = 0.0; s.range = 0.0;
+  // defaults of the fields HowFar defines (G4HepEmTrack::ReSet / G4HepEmMSCTrackData::ReSet values); the energy
+  // deposit is not one of them: HowFar leaves what the previous Perform wrote
+  s.winner = -1; s.gStep = 0.0; s.pStep = 0.0; s.edep = LoadPair(b.edep_dispx, i).a; s.range = 0.0;
   s.mfp[0] = s.mfp[1] = s.mfp[2] = s.mfp[3] = -1.0;
   s.lambtr1 = 0.0; s.trueStep = 0.0; s.zPath = 0.0;
   s.disp[0] = s.disp[1] = s.disp[2] = 0.0;
@@ -155,7 +156,10 @@ G4H_FN void LoadGamma(const G4HB200GammaBatch& b, int64_t i, uint64_t seed, Gamm
   s.imc = m.imc; s.id = m.id;
   s.onBoundary = (static_cast<uint32_t>(m.flags) & G4HB200_F_ON_BOUNDARY) != 0u;
   rng.Init(seed, static_cast<uint32_t>(m.id), static_cast<uint32_t>(m.draw), false, 0.0);
-  s.mfp0 = -1.0; s.gStep = 0.0; s.edep = 0.0; s.peMXsec = 0.0; s.winner = -1;
+  // fields HowFar does not define keep what the previous step left in the track (the reference's managers work
+  // in place on a persistent G4HepEmGammaTrack): winner index, deposit, fPEmxSec
+  const Pair ep = LoadPair(b.edep_pemxsec, i);
+  s.mfp0 = -1.0; s.gStep = 0.0; s.edep = ep.a; s.peMXsec = ep.b; s.winner = b.winner[i];
 }
 
 G4H_FN void LoadGammaHandOver(const G4HB200GammaBatch& b, int64_t i, GammaState& s) {

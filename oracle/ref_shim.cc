@@ -92,10 +92,11 @@ void UnpackElectron(const G4HB200ElectronBatch* b, int64_t i, G4HepEmElectronTra
   stream.draw     = static_cast<uint32_t>(meta[3]);
   eng.fIsGauss = Has(flags, G4HB200_F_GAUSS_CACHED);
   eng.fGauss   = b->msc_tlimmin_gauss[2 * i + 1];
+  // a track object persists between the calls: HowFar does not touch the deposit of the previous step
+  t->SetEnergyDeposit(b->edep_dispx[2 * i]);
   if (withHandOver) {
     t->SetGStepLength(b->gstep_pstep[2 * i]);
     et.SetPStepLength(b->gstep_pstep[2 * i + 1]);
-    t->SetEnergyDeposit(b->edep_dispx[2 * i]);
     msc->SetDisplacement(b->edep_dispx[2 * i + 1], b->dispy_dispz[2 * i], b->dispy_dispz[2 * i + 1]);
     t->SetWinnerProcessIndex(b->winner[i]);
     t->SetMFP(b->mfp01[2 * i], 0);
@@ -189,12 +190,13 @@ void UnpackGamma(const G4HB200GammaBatch* b, int64_t i, G4HepEmGammaTrack& gt, G
   stream.seed     = seed;
   stream.track_id = static_cast<uint32_t>(meta[2]);
   stream.draw     = static_cast<uint32_t>(meta[3]);
+  // persistent between the calls (a stale winner index survives a boundary-limited step in the reference)
+  t->SetEnergyDeposit(b->edep_pemxsec[2 * i]);
+  gt.SetPEmxSec(b->edep_pemxsec[2 * i + 1]);
+  t->SetWinnerProcessIndex(b->winner[i]);
   if (withHandOver) {
     t->SetGStepLength(b->gstep_mfp0[2 * i]);
     t->SetMFP(b->gstep_mfp0[2 * i + 1], 0);
-    t->SetEnergyDeposit(b->edep_pemxsec[2 * i]);
-    gt.SetPEmxSec(b->edep_pemxsec[2 * i + 1]);
-    t->SetWinnerProcessIndex(b->winner[i]);
   }
 }
 

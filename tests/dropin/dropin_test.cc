@@ -75,7 +75,7 @@ int CompareSecondaries(std::vector<Sec>& a, const std::vector<G4HepEmB200Seconda
 }
 
 bool SameTrack(G4HepEmTrack* a, G4HepEmTrack* b) {
-  bool ok = Close(a->GetEKin(), b->GetEKin()) && Close(a->GetEnergyDeposit(), b->GetEnergyDeposit()) &&
+  bool ok = Close(a->GetEKin(), b->GetEKin()) && Close(a->GetEnergyDeposit(), b->GetEnergyDeposit()) && Close(a->GetMFP(0), b->GetMFP(0)) &&
             Close(a->GetGStepLength(), b->GetGStepLength()) && a->GetWinnerProcessIndex() == b->GetWinnerProcessIndex();
   for (int d = 0; d < 3; ++d) ok = ok && CloseAbs(a->GetDirection()[d], b->GetDirection()[d], 1.0);
   for (int p = 0; p < 4; ++p) ok = ok && Close(a->GetNumIALeft(p), b->GetNumIALeft(p));

@@ -143,6 +143,7 @@ class SecondaryQueue(C.Structure):
         ("parent_kind", c_ip),
         ("parent_slot", c_ip),
         ("count", c_ip),
+        ("parent_base", C.c_int32),
     ]
 
 

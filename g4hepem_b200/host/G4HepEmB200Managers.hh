@@ -135,6 +135,7 @@ class G4HepEmB200Session {
       view.parent_kind = pk.data();
       view.parent_slot = ps.data();
       view.count = count;
+      view.parent_base = 0;
     }
   };
 

@@ -191,6 +191,7 @@ typedef struct G4HB200SecondaryQueue {
   int32_t* parent_kind; /* int2: {parent fID, G4HB200_SEC_*}; slot order within a parent is preserved */
   int32_t* parent_slot; /* int2: {index of the parent track in its batch, 0/1 = first/second secondary} */
   int32_t* count;     /* [1] number of valid entries */
+  int32_t parent_base; /* added to the parent index written by the kernels (a batch processed in chunks); normally 0 */
 } G4HB200SecondaryQueue;
 
 typedef struct G4HB200 G4HB200; /* opaque handle: device arena with the flattened tables */

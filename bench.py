@@ -43,7 +43,9 @@ WRITE_BYTES = 10 * 16 + 16 + 4     # persistent + 3 result groups + meta + winne
 SEC_BYTES = 16 + 16 + 8 + 8        # one secondary record
 # algorithmic bytes per track of every pipeline stage: (read, written, secondaries appended); DESIGN.md par. 4
 STAGE_BYTES = {
-    "ElectronKernel<0> (HowFar)": (7 * 16 + 16, 10 * 16 + 16 + 4 + 6 * 16, 0),
+    # (bytes read, bytes written, secondaries) per track a stage processes; 16 B per {a,b} group, 16 B meta, 4 B winner
+    "ElHowFarXSKernel": (3 * 16 + 16, 7 * 16 + 16 + 4, 0),
+    "ElHowFarMSCKernel": (6 * 16 + 16 + 4, 6 * 16 + 16 + 4, 0),
     "ElContinuousKernel": (7 * 16 + 16 + 9 * 16 + 4, 10 * 16 + 16 + 4 + 16 + 16, 0),
     "ElFluctuationKernel": (4 + 16 + 3 * 16 + 4, 3 * 16 + 16, 0),
     "ElDiscreteKernel": (4 + 16 + 16 + 4 + 16 + 16, 3 * 16, 0),

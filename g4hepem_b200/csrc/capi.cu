@@ -118,7 +118,8 @@ struct G4HB200 {
   // per-kernel timing (g4hb200_set_kernel_timing): one event row per timed pipeline call
   bool timing = false;
   struct TimedCall {
-    cudaEvent_t ev[G4HB200_NUM_STAGES + 1];
+    cudaEvent_t ev[2 * G4HB200_NUM_STAGES];  // {before, after} per stage
+    cudaEvent_t done;
     bool ran[G4HB200_NUM_STAGES];
     int32_t* counts;  // pinned copy of the queue counters of that call
     int64_t n;
@@ -268,6 +269,77 @@ int EnsureElectronWork(G4HB200::WorkSlot& slot, int64_t n) {
   return 0;
 }
 
+// pipeline stages of the e-/e+ step, in launch order (g4h_pipeline.cuh)
+enum ElStage {
+  kSHowFarXS = 0, kSHowFarMSC, kSContinuous, kSFluct, kSDiscrete, kSMoller, kSBhabha, kSSB, kSRB, kSAnnih, kSAtRest,
+  kNumElStages
+};
+static_assert(kNumElStages <= G4HB200_NUM_STAGES, "G4HB200_NUM_STAGES too small");
+// pipeline stage -> queue that feeds it (-1: every track of the batch)
+const int kStageQueue[G4HB200_NUM_STAGES] = {-1, -1, -1, kQFluct, kQDiscrete, kQMoller, kQBhabha, kQSB, kQRB, kQAnnih, kQAtRest,
+                                             -1, -1, -1, -1, -1};
+const char* const kStageName[G4HB200_NUM_STAGES] = {
+    "ElHowFarXSKernel", "ElHowFarMSCKernel", "ElContinuousKernel", "ElFluctuationKernel", "ElDiscreteKernel",
+    "ElSamplerKernel<Moller>", "ElSamplerKernel<Bhabha>", "ElSamplerKernel<SeltzerBerger>", "ElSamplerKernel<RelBrem>",
+    "ElSamplerKernel<Annihilation>", "ElSamplerKernel<AtRest>", "", "", "", "", ""};
+
+struct StageTimer {
+  G4HB200* h;
+  cudaStream_t st;
+  G4HB200::TimedCall* tc = nullptr;
+  cudaError_t Begin(int64_t n) {
+    if (!h->timing) return cudaSuccess;
+    h->timed.emplace_back();
+    tc = &h->timed.back();
+    tc->n = n;
+    tc->counts = nullptr;
+    for (auto& r : tc->ran) r = false;
+    for (auto& e : tc->ev) {
+      const cudaError_t err = cudaEventCreate(&e);
+      if (err != cudaSuccess) return err;
+    }
+    cudaError_t err = cudaEventCreate(&tc->done);
+    if (err != cudaSuccess) return err;
+    err = cudaMallocHost(reinterpret_cast<void**>(&tc->counts), kNumElQueues * sizeof(int32_t));
+    if (err != cudaSuccess) return err;
+    for (int k = 0; k < kNumElQueues; ++k) tc->counts[k] = 0;
+    return cudaSuccess;
+  }
+  // bracket one launch: Before(stage) ... kernel ... After(stage)
+  cudaError_t Before(int stage) { return tc != nullptr ? cudaEventRecord(tc->ev[2 * stage], st) : cudaSuccess; }
+  cudaError_t After(int stage) {
+    ++h->launches;
+    if (tc == nullptr) return cudaGetLastError();
+    tc->ran[stage] = true;
+    return cudaEventRecord(tc->ev[2 * stage + 1], st);
+  }
+};
+
+// G4HepEmElectronManager::HowFar as two kernels (g4h_stages.cuh)
+template <bool kStoreResults>
+int LaunchHowFarStages(G4HB200* h, G4HB200ElectronBatch* dev, uint64_t seed, cudaStream_t st, StageTimer& t) {
+  const int grid = GridFor(dev->n, h->smCount, 8);
+  G4H_CUDA(t.Before(kSHowFarXS));
+  ElHowFarXSKernel<<<grid, kThreadsPerBlock, 0, st>>>(h->view, *dev, seed);
+  G4H_CUDA(t.After(kSHowFarXS));
+  G4H_CUDA(t.Before(kSHowFarMSC));
+  ElHowFarMSCKernel<kStoreResults><<<grid, kThreadsPerBlock, 0, st>>>(h->view, *dev, seed);
+  G4H_CUDA(t.After(kSHowFarMSC));
+  return 0;
+}
+
+int LaunchElectronHowFar(G4HB200* h, G4HB200ElectronBatch* dev, uint64_t seed, void* stream) {
+  int rc = CheckHandle(h);
+  if (rc != 0) return rc;
+  if (dev == nullptr || dev->n < 0) return Fail(G4HB200_EINVAL, "bad electron batch");
+  if (dev->n == 0) return 0;
+  StageTimer t{h, static_cast<cudaStream_t>(stream)};
+  rc = LaunchHowFarStages<true>(h, dev, seed, t.st, t);
+  if (rc != 0) return rc;
+  G4H_CUDA(cudaGetLastError());
+  return 0;
+}
+
 // G4HepEmElectronManager::Perform as a pipeline (g4h_pipeline.cuh); kFused: HowFar first
 template <bool kFused>
 int LaunchElectronPipeline(G4HB200* h, G4HB200ElectronBatch* dev, G4HB200SecondaryQueue* sec, uint64_t seed, void* stream,
@@ -283,61 +355,30 @@ int LaunchElectronPipeline(G4HB200* h, G4HB200ElectronBatch* dev, G4HB200Seconda
   const int grid = GridFor(dev->n, h->smCount, 8);
   const ElectronWork& w = h->slots[slotIndex].work;
   G4H_CUDA(cudaMemsetAsync(w.count, 0, kNumElQueues * sizeof(int32_t), st));
-  G4HB200::TimedCall* tc = nullptr;
-  if (h->timing) {
-    h->timed.emplace_back();
-    tc = &h->timed.back();
-    tc->n = dev->n;
-    tc->counts = nullptr;
-    for (auto& e : tc->ev) G4H_CUDA(cudaEventCreate(&e));
-    for (auto& r : tc->ran) r = false;
-    G4H_CUDA(cudaMallocHost(reinterpret_cast<void**>(&tc->counts), kNumElQueues * sizeof(int32_t)));
-    G4H_CUDA(cudaEventRecord(tc->ev[0], st));
-  }
-  int stage = 0;
-  auto done = [&](bool ran) -> cudaError_t {
-    if (ran) ++h->launches;
-    if (tc != nullptr) {
-      tc->ran[stage] = ran;
-      const cudaError_t e = cudaEventRecord(tc->ev[stage + 1], st);
-      if (e != cudaSuccess) return e;
-    }
-    ++stage;
-    return cudaSuccess;
-  };
-  if (kFused) ElectronKernel<0><<<grid, kThreadsPerBlock, 0, st>>>(h->view, *dev, NullQueue(), seed);
-  G4H_CUDA(done(kFused));
-  ElContinuousKernel<<<grid, kThreadsPerBlock, 0, st>>>(h->view, *dev, w, seed);
-  G4H_CUDA(done(true));
-  ElFluctuationKernel<<<grid, kThreadsPerBlock, 0, st>>>(h->view, *dev, w, seed);
-  G4H_CUDA(done(true));
-  ElDiscreteKernel<<<grid, kThreadsPerBlock, 0, st>>>(h->view, *dev, w, seed);
-  G4H_CUDA(done(true));
-  ElSamplerKernel<kQMoller><<<grid, kThreadsPerBlock, 0, st>>>(h->view, *dev, w, *sec, seed);
-  G4H_CUDA(done(true));
-  ElSamplerKernel<kQBhabha><<<grid, kThreadsPerBlock, 0, st>>>(h->view, *dev, w, *sec, seed);
-  G4H_CUDA(done(true));
-  ElSamplerKernel<kQSB><<<grid, kThreadsPerBlock, 0, st>>>(h->view, *dev, w, *sec, seed);
-  G4H_CUDA(done(true));
-  ElSamplerKernel<kQRB><<<grid, kThreadsPerBlock, 0, st>>>(h->view, *dev, w, *sec, seed);
-  G4H_CUDA(done(true));
-  ElSamplerKernel<kQAnnih><<<grid, kThreadsPerBlock, 0, st>>>(h->view, *dev, w, *sec, seed);
-  G4H_CUDA(done(true));
-  ElSamplerKernel<kQAtRest><<<grid, kThreadsPerBlock, 0, st>>>(h->view, *dev, w, *sec, seed);
-  G4H_CUDA(done(true));
-  if (tc != nullptr) {
-    G4H_CUDA(cudaMemcpyAsync(tc->counts, w.count, kNumElQueues * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+  StageTimer t{h, st};
+  G4H_CUDA(t.Begin(dev->n));
+  if (kFused && (rc = LaunchHowFarStages<true>(h, dev, seed, st, t)) != 0) return rc;
+#define G4H_STAGE(stage, ...)       \
+  G4H_CUDA(t.Before(stage));        \
+  __VA_ARGS__;                      \
+  G4H_CUDA(t.After(stage))
+  G4H_STAGE(kSContinuous, ElContinuousKernel<<<grid, kThreadsPerBlock, 0, st>>>(h->view, *dev, w, seed));
+  G4H_STAGE(kSFluct, ElFluctuationKernel<<<grid, kThreadsPerBlock, 0, st>>>(h->view, *dev, w, seed));
+  G4H_STAGE(kSDiscrete, ElDiscreteKernel<<<grid, kThreadsPerBlock, 0, st>>>(h->view, *dev, w, seed));
+  G4H_STAGE(kSMoller, ElSamplerKernel<kQMoller><<<grid, kThreadsPerBlock, 0, st>>>(h->view, *dev, w, *sec, seed));
+  G4H_STAGE(kSBhabha, ElSamplerKernel<kQBhabha><<<grid, kThreadsPerBlock, 0, st>>>(h->view, *dev, w, *sec, seed));
+  G4H_STAGE(kSSB, ElSamplerKernel<kQSB><<<grid, kThreadsPerBlock, 0, st>>>(h->view, *dev, w, *sec, seed));
+  G4H_STAGE(kSRB, ElSamplerKernel<kQRB><<<grid, kThreadsPerBlock, 0, st>>>(h->view, *dev, w, *sec, seed));
+  G4H_STAGE(kSAnnih, ElSamplerKernel<kQAnnih><<<grid, kThreadsPerBlock, 0, st>>>(h->view, *dev, w, *sec, seed));
+  G4H_STAGE(kSAtRest, ElSamplerKernel<kQAtRest><<<grid, kThreadsPerBlock, 0, st>>>(h->view, *dev, w, *sec, seed));
+#undef G4H_STAGE
+  if (t.tc != nullptr) {
+    G4H_CUDA(cudaMemcpyAsync(t.tc->counts, w.count, kNumElQueues * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    G4H_CUDA(cudaEventRecord(t.tc->done, st));
   }
   G4H_CUDA(cudaGetLastError());
   return 0;
 }
-
-// pipeline stage -> queue that feeds it (-1: every track of the batch)
-const int kStageQueue[G4HB200_NUM_STAGES] = {-1, -1, kQFluct, kQDiscrete, kQMoller, kQBhabha, kQSB, kQRB, kQAnnih, kQAtRest};
-const char* const kStageName[G4HB200_NUM_STAGES] = {
-    "ElectronKernel<0> (HowFar)", "ElContinuousKernel", "ElFluctuationKernel", "ElDiscreteKernel", "ElSamplerKernel<Moller>",
-    "ElSamplerKernel<Bhabha>", "ElSamplerKernel<SeltzerBerger>", "ElSamplerKernel<RelBrem>", "ElSamplerKernel<Annihilation>",
-    "ElSamplerKernel<AtRest>"};
 
 }  // namespace
 
@@ -694,7 +735,8 @@ int g4hb200_rng_uniforms(G4HB200* h, uint64_t seed, int64_t n, const int32_t* tr
 }
 
 int g4hb200_electron_howfar(G4HB200* h, G4HB200ElectronBatch* dev, uint64_t seed, void* stream) {
-  return LaunchElectron<0>(h, dev, nullptr, seed, stream);
+  if (h != nullptr && h->monolith) return LaunchElectron<0>(h, dev, nullptr, seed, stream);
+  return LaunchElectronHowFar(h, dev, seed, stream);
 }
 int g4hb200_electron_perform(G4HB200* h, G4HB200ElectronBatch* dev, G4HB200SecondaryQueue* sec, uint64_t seed, void* stream) {
   if (h != nullptr && h->monolith) return LaunchElectron<1>(h, dev, sec, seed, stream);
@@ -870,16 +912,17 @@ int g4hb200_kernel_times(G4HB200* h, double* ms_sum, int64_t* launches, int64_t*
     items[k] = 0;
   }
   for (auto& tc : h->timed) {
-    G4H_CUDA(cudaEventSynchronize(tc.ev[G4HB200_NUM_STAGES]));
+    G4H_CUDA(cudaEventSynchronize(tc.done));
     for (int k = 0; k < G4HB200_NUM_STAGES; ++k) {
       if (!tc.ran[k]) continue;
       float ms = 0.f;
-      G4H_CUDA(cudaEventElapsedTime(&ms, tc.ev[k], tc.ev[k + 1]));
+      G4H_CUDA(cudaEventElapsedTime(&ms, tc.ev[2 * k], tc.ev[2 * k + 1]));
       ms_sum[k] += ms;
       launches[k] += 1;
       items[k] += kStageQueue[k] < 0 ? tc.n : tc.counts[kStageQueue[k]];
     }
     for (auto& e : tc.ev) cudaEventDestroy(e);
+    cudaEventDestroy(tc.done);
     cudaFreeHost(tc.counts);
   }
   h->timed.clear();

@@ -209,15 +209,22 @@ G4H_FN void EvaluateLPMFunctions(double& funcXiS, double& funcGS, double& funcPh
   }
 }
 
-// Brem::LinSearch (Brem.icc:328-344): first index (stride 3) whose cumulative exceeds val
+// Brem::LinSearch (Brem.icc:328-344): first index (stride 3) whose cumulative exceeds val.  The reference scans
+// the 54 kappa points linearly (up to 54 dependent loads); the cumulative is non-decreasing by construction
+// (Init/src/G4HepEmElectronTableBuilder.cc:685-834), so the upper bound found by bisection (6 loads) is the same index.
 G4H_FN int SBLinSearch(const double* vect, int size, double val) {
-  int i = 0;
-  const int size3 = 3 * size;
-  while (i < size3) {
-    if (G4H_LD(vect + i) > val) break;
-    i += 3;
+  int lo  = 0;
+  int len = size;
+  while (len > 0) {
+    const int half = len >> 1;
+    if (G4H_LD(vect + 3 * (lo + half)) > val) {
+      len = half;
+    } else {
+      lo += half + 1;
+      len -= half + 1;
+    }
   }
-  return i;
+  return 3 * lo;
 }
 
 // SampleETransferSB (Brem.icc:73-182)

@@ -26,11 +26,31 @@ constexpr int kThreadsPerBlock = 256;
 #define G4H_MINB_QUEUE 2
 #endif
 
-// ---- warp aggregated append to the secondary queue -------------------------------------------------------
-// called by all 32 lanes of a warp (sec.n may be 0): ballots give each lane its offset, one atomicAdd per
-// warp reserves the slots
-__device__ __forceinline__ void AppendSecondaries(const G4HB200SecondaryQueue& q, const Secondaries& sec, int parentId,
-                                                  int64_t parentIndex) {
+// ---- CTA aggregated appends ----------------------------------------------------------------------------------
+// Same-address global atomics serialise in L2: with one atomicAdd per warp the queue counters were the
+// hottest lines of the queue kernels (40 % of the stall samples of ElDiscreteKernel, profiles/r01_*).  Appends
+// are therefore aggregated per CTA: warps reserve their share in a shared-memory counter, one thread
+// reserves the CTA's range with a single global atomicAdd.  Every thread of the CTA must call these (loops
+// run a CTA-uniform number of iterations), they contain two __syncthreads().
+
+template <int K>
+struct CtaCounters {
+  int count[K];  // zero between calls
+  int base[K];
+  __device__ __forceinline__ void Init() {
+    if (threadIdx.x < K) count[threadIdx.x] = 0;
+    __syncthreads();
+  }
+};
+
+// loop bound of a grid-stride loop in which every thread of a CTA runs the same number of iterations
+__device__ __forceinline__ int64_t RoundUpToCta(int64_t n) {
+  return ((n + blockDim.x - 1) / blockDim.x) * blockDim.x;
+}
+
+// secondaries: sec.n in {0,1,2} per thread
+__device__ __forceinline__ void AppendSecondaries(CtaCounters<1>& cc, const G4HB200SecondaryQueue& q, const Secondaries& sec,
+                                                  int parentId, int64_t parentIndex) {
   const unsigned active = 0xffffffffu;
   const int lane = threadIdx.x & 31;
   const unsigned has1 = __ballot_sync(active, sec.n >= 1);
@@ -38,12 +58,19 @@ __device__ __forceinline__ void AppendSecondaries(const G4HB200SecondaryQueue& q
   const unsigned below = (1u << lane) - 1u;
   const int excl  = __popc(has1 & below) + __popc(has2 & below);
   const int total = __popc(has1) + __popc(has2);
-  if (total == 0) return;
-  int base = 0;
-  if (lane == 0) base = atomicAdd(q.count, total);
-  base = __shfl_sync(active, base, 0);
+  int warpBase = 0;
+  if (lane == 0 && total > 0) warpBase = atomicAdd(&cc.count[0], total);
+  warpBase = __shfl_sync(active, warpBase, 0);
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const int t = cc.count[0];
+    cc.base[0]  = t > 0 ? atomicAdd(q.count, t) : 0;
+    cc.count[0] = 0;
+  }
+  __syncthreads();
+  const int64_t base = static_cast<int64_t>(cc.base[0]) + warpBase + excl;
   for (int k = 0; k < sec.n; ++k) {
-    const int64_t slot = static_cast<int64_t>(base) + excl + k;
+    const int64_t slot = base + k;
     if (slot < q.capacity) {
       reinterpret_cast<double2*>(q.dirx_diry)[slot] = make_double2(sec.s[k].dir[0], sec.s[k].dir[1]);
       reinterpret_cast<double2*>(q.dirz_ekin)[slot] = make_double2(sec.s[k].dir[2], sec.s[k].ekin);
@@ -53,6 +80,34 @@ __device__ __forceinline__ void AppendSecondaries(const G4HB200SecondaryQueue& q
   }
 }
 
+// track index -> one of K queues: route in [0,K) or -1 (none); the k-th queue is queues[first + k] with its
+// global counter counts + first + k
+template <int K>
+__device__ __forceinline__ void RouteToQueues(CtaCounters<K>& cc, int route, int32_t value, int32_t* const* queues,
+                                              int32_t* counts) {
+  const unsigned active = 0xffffffffu;
+  const int lane = threadIdx.x & 31;
+  int offset = 0;
+#pragma unroll
+  for (int k = 0; k < K; ++k) {
+    const unsigned m = __ballot_sync(active, route == k);
+    if (m != 0u) {
+      int wb = 0;
+      if (lane == 0) wb = atomicAdd(&cc.count[k], __popc(m));
+      wb = __shfl_sync(active, wb, 0);
+      if (route == k) offset = wb + __popc(m & ((1u << lane) - 1u));
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x < K) {
+    const int t = cc.count[threadIdx.x];
+    cc.base[threadIdx.x]  = t > 0 ? atomicAdd(counts + threadIdx.x, t) : 0;
+    cc.count[threadIdx.x] = 0;
+  }
+  __syncthreads();
+  if (route >= 0) queues[route][cc.base[route] + offset] = value;
+}
+
 // ---- e-/e+ ---------------------------------------------------------------------------------------------------
 // mode 0: HowFar, 1: Perform, 2: fused HowFar + Perform
 template <int kMode>
@@ -60,8 +115,10 @@ __global__ void __launch_bounds__(kThreadsPerBlock, kMode == 0 ? G4H_MINB_HOWFAR
 ElectronKernel(const __grid_constant__ TablesView tv, const __grid_constant__ G4HB200ElectronBatch b,
                const __grid_constant__ G4HB200SecondaryQueue q, uint64_t seed) {
   const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
-  // the loop bound is rounded up to a full warp so that whole warps reach the aggregated append
-  const int64_t nRound = (b.n + 31) & ~static_cast<int64_t>(31);
+  // the loop bound is rounded up to a full CTA so that whole CTAs reach the aggregated append
+  const int64_t nRound = RoundUpToCta(b.n);
+  __shared__ CtaCounters<1> cc;
+  if (kMode != 0) cc.Init();
   for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < nRound; i += stride) {
     const bool valid = i < b.n;
     ElectronState s;
@@ -84,10 +141,7 @@ ElectronKernel(const __grid_constant__ TablesView tv, const __grid_constant__ G4
       // Perform re-converts the geometrical step when geometry cut it (UpdatePStepLength): fTrueStepLength / fZPathLength
       if (kMode == 1) StorePair(b.tstep_zpath, i, s.trueStep, s.zPath);
     }
-    if (kMode != 0) {
-      __syncwarp();
-      AppendSecondaries(q, sec, valid ? s.id : 0, i);
-    }
+    if (kMode != 0) AppendSecondaries(cc, q, sec, valid ? s.id : 0, i);
   }
 }
 
@@ -97,7 +151,9 @@ __global__ void __launch_bounds__(kThreadsPerBlock)
 GammaKernel(const __grid_constant__ TablesView tv, const __grid_constant__ G4HB200GammaBatch b,
             const __grid_constant__ G4HB200SecondaryQueue q, uint64_t seed) {
   const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
-  const int64_t nRound = (b.n + 31) & ~static_cast<int64_t>(31);
+  const int64_t nRound = RoundUpToCta(b.n);
+  __shared__ CtaCounters<1> cc;
+  if (kMode != 0) cc.Init();
   for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < nRound; i += stride) {
     const bool valid = i < b.n;
     GammaState s;
@@ -112,10 +168,7 @@ GammaKernel(const __grid_constant__ TablesView tv, const __grid_constant__ G4HB2
       if (kMode != 0) GammaPerform(tv, s, rng, sec);
       StoreGamma(b, i, s, rng, flags);
     }
-    if (kMode != 0) {
-      __syncwarp();
-      AppendSecondaries(q, sec, valid ? s.id : 0, i);
-    }
+    if (kMode != 0) AppendSecondaries(cc, q, sec, valid ? s.id : 0, i);
   }
 }
 

@@ -12,14 +12,15 @@
 //                                                                               -> queues: one per model
 //   ElSamplerKernel<K>   queue K: Moller | Bhabha | Seltzer-Berger | rel. brem | annihilation in flight | at rest
 //
-// Queues are arrays of track indices in the handle's workspace, filled with one atomicAdd per warp
-// (ballot + popc); results go back to the track's own slot, so the outcome does not depend on queue order.
+// Queues are arrays of track indices in the handle's workspace, filled with one global atomicAdd per CTA
+// and queue (warp ballots + a shared-memory counter, g4h_kernels.cuh); results go back to the track's own slot, so the outcome does not depend on queue order.
 // Between kernels the track lives in its batch groups plus one workspace group (the pre-step energy).
 // The uniform stream is keyed by (seed, track id, draw counter), the counter travels in meta[3].
 #ifndef G4H_PIPELINE_CUH
 #define G4H_PIPELINE_CUH
 
 #include "g4h_kernels.cuh"
+#include "g4h_stages.cuh"
 
 namespace g4h {
 
@@ -31,16 +32,28 @@ struct ElectronWork {
   int32_t* count;                 // [kNumElQueues]
 };
 
-// all 32 lanes of the warp call this; lanes with pred append value
-__device__ __forceinline__ void QueuePush(int32_t* __restrict__ q, int32_t* __restrict__ count, bool pred, int32_t value) {
-  const unsigned m = __ballot_sync(0xffffffffu, pred);
-  if (m == 0u) return;
-  const int lane   = threadIdx.x & 31;
-  const int leader = __ffs(m) - 1;
-  int base = 0;
-  if (lane == leader) base = atomicAdd(count, __popc(m));
-  base = __shfl_sync(0xffffffffu, base, leader);
-  if (pred) q[base + __popc(m & ((1u << lane) - 1u))] = value;
+// ---- HowFar in two stages (g4h_stages.cuh) ---------------------------------------------------------------------
+#ifndef G4H_MINB_XS
+#define G4H_MINB_XS 3
+#endif
+#ifndef G4H_MINB_MSCLIM
+#define G4H_MINB_MSCLIM 3
+#endif
+__global__ void __launch_bounds__(kThreadsPerBlock, G4H_MINB_XS)
+ElHowFarXSKernel(const __grid_constant__ TablesView tv, const __grid_constant__ G4HB200ElectronBatch b, uint64_t seed) {
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < b.n; i += stride) {
+    StageHowFarXS(tv, b, i, seed);
+  }
+}
+
+template <bool kStoreResults>
+__global__ void __launch_bounds__(kThreadsPerBlock, G4H_MINB_MSCLIM)
+ElHowFarMSCKernel(const __grid_constant__ TablesView tv, const __grid_constant__ G4HB200ElectronBatch b, uint64_t seed) {
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < b.n; i += stride) {
+    StageHowFarMSC<kStoreResults>(tv, b, i, seed);
+  }
 }
 
 // ---- continuous part for every track --------------------------------------------------------------------------
@@ -48,7 +61,9 @@ __global__ void __launch_bounds__(kThreadsPerBlock, G4H_MINB_CONT)
 ElContinuousKernel(const __grid_constant__ TablesView tv, const __grid_constant__ G4HB200ElectronBatch b,
                    const __grid_constant__ ElectronWork w, uint64_t seed) {
   const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
-  const int64_t nRound = (b.n + 31) & ~static_cast<int64_t>(31);
+  const int64_t nRound = RoundUpToCta(b.n);
+  __shared__ CtaCounters<3> cc;
+  cc.Init();
   for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < nRound; i += stride) {
     int route = -1;
     if (i < b.n) {
@@ -94,10 +109,8 @@ ElContinuousKernel(const __grid_constant__ TablesView tv, const __grid_constant_
       StoreElectron(b, i, s, rng);
       StorePair(b.tstep_zpath, i, s.trueStep, s.zPath);
     }
-    const int32_t idx = static_cast<int32_t>(i);
-    QueuePush(w.queue[kQFluct], w.count + kQFluct, route == kQFluct, idx);
-    QueuePush(w.queue[kQDiscrete], w.count + kQDiscrete, route == kQDiscrete, idx);
-    QueuePush(w.queue[kQAtRest], w.count + kQAtRest, route == kQAtRest, idx);
+    // kQFluct, kQDiscrete, kQAtRest are queues 0..2
+    RouteToQueues<3>(cc, route, static_cast<int32_t>(i), w.queue, w.count);
   }
 }
 
@@ -106,8 +119,10 @@ __global__ void __launch_bounds__(kThreadsPerBlock, G4H_MINB_QUEUE)
 ElFluctuationKernel(const __grid_constant__ TablesView tv, const __grid_constant__ G4HB200ElectronBatch b,
                     const __grid_constant__ ElectronWork w, uint64_t seed) {
   const int cnt = w.count[kQFluct];
-  const int nRound = (cnt + 31) & ~31;
+  const int nRound = static_cast<int>(RoundUpToCta(cnt));
   const int stride = gridDim.x * blockDim.x;
+  __shared__ CtaCounters<2> cc;
+  cc.Init();
   for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < nRound; q += stride) {
     int route = -1;
     int32_t i = 0;
@@ -136,8 +151,7 @@ ElFluctuationKernel(const __grid_constant__ TablesView tv, const __grid_constant
         route = kQDiscrete;
       }
     }
-    QueuePush(w.queue[kQDiscrete], w.count + kQDiscrete, route == kQDiscrete, i);
-    QueuePush(w.queue[kQAtRest], w.count + kQAtRest, route == kQAtRest, i);
+    RouteToQueues<2>(cc, route - kQDiscrete, i, w.queue + kQDiscrete, w.count + kQDiscrete);
   }
 }
 
@@ -146,8 +160,10 @@ __global__ void __launch_bounds__(kThreadsPerBlock, G4H_MINB_QUEUE)
 ElDiscreteKernel(const __grid_constant__ TablesView tv, const __grid_constant__ G4HB200ElectronBatch b,
                  const __grid_constant__ ElectronWork w, uint64_t seed) {
   const int cnt = w.count[kQDiscrete];
-  const int nRound = (cnt + 31) & ~31;
+  const int nRound = static_cast<int>(RoundUpToCta(cnt));
   const int stride = gridDim.x * blockDim.x;
+  __shared__ CtaCounters<5> cc;
+  cc.Init();
   for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < nRound; q += stride) {
     int route = -1;
     int32_t i = 0;
@@ -186,11 +202,8 @@ ElDiscreteKernel(const __grid_constant__ TablesView tv, const __grid_constant__ 
         }
       }
     }
-    QueuePush(w.queue[kQMoller], w.count + kQMoller, route == kQMoller, i);
-    QueuePush(w.queue[kQBhabha], w.count + kQBhabha, route == kQBhabha, i);
-    QueuePush(w.queue[kQSB], w.count + kQSB, route == kQSB, i);
-    QueuePush(w.queue[kQRB], w.count + kQRB, route == kQRB, i);
-    QueuePush(w.queue[kQAnnih], w.count + kQAnnih, route == kQAnnih, i);
+    // kQMoller .. kQAnnih are five consecutive queues
+    RouteToQueues<5>(cc, route < 0 ? -1 : route - kQMoller, i, w.queue + kQMoller, w.count + kQMoller);
   }
 }
 
@@ -200,8 +213,10 @@ __global__ void __launch_bounds__(kThreadsPerBlock, G4H_MINB_QUEUE)
 ElSamplerKernel(const __grid_constant__ TablesView tv, const __grid_constant__ G4HB200ElectronBatch b,
                 const __grid_constant__ ElectronWork w, const __grid_constant__ G4HB200SecondaryQueue sq, uint64_t seed) {
   const int cnt = w.count[kQueue];
-  const int nRound = (cnt + 31) & ~31;
+  const int nRound = static_cast<int>(RoundUpToCta(cnt));
   const int stride = gridDim.x * blockDim.x;
+  __shared__ CtaCounters<1> cc;
+  cc.Init();
   for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < nRound; q += stride) {
     Secondaries sec;
     sec.n = 0;
@@ -234,8 +249,7 @@ ElSamplerKernel(const __grid_constant__ TablesView tv, const __grid_constant__ G
       }
       StoreMeta(b.meta, i, Meta{m.imc, m.flags, m.id, static_cast<int>(rng.draw)});
     }
-    __syncwarp();
-    AppendSecondaries(sq, sec, id, i);
+    AppendSecondaries(cc, sq, sec, id, i);
   }
 }
 

@@ -108,8 +108,8 @@ G4H_FN int LogBin(double logx, double logxmin, double invLDBin, int ndata) {
 }
 
 // GetSplineLog, y and second derivative interleaved, separate x grid (G4HepEmRunUtils.icc:86-93)
-G4H_LEAF double SplineLogYSD(int ndata, const double* xdata, const double* ydata, double x, double logx, double logxmin,
-                           double invLDBin) {
+G4H_FN double SplineLogYSDInl(int ndata, const double* xdata, const double* ydata, double x, double logx, double logxmin,
+                              double invLDBin) {
   const double xv = Max(G4H_LD(xdata), Min(G4H_LD(xdata + ndata - 1), x));
   const int idx   = LogBin(logx, logxmin, invLDBin, ndata);
   const int idx2  = 2 * idx;
@@ -117,13 +117,22 @@ G4H_LEAF double SplineLogYSD(int ndata, const double* xdata, const double* ydata
                 G4H_LD(ydata + idx2 + 1), G4H_LD(ydata + idx2 + 3), xv);
 }
 
+G4H_LEAF double SplineLogYSD(int ndata, const double* xdata, const double* ydata, double x, double logx, double logxmin,
+                             double invLDBin) {
+  return SplineLogYSDInl(ndata, xdata, ydata, x, logx, logxmin, invLDBin);
+}
+
 // GetSplineLog, x, y and second derivative interleaved (G4HepEmRunUtils.icc:97-104)
-G4H_LEAF double SplineLogXYSD(int ndata, const double* data, double x, double logx, double logxmin, double invLDBin) {
+G4H_FN double SplineLogXYSDInl(int ndata, const double* data, double x, double logx, double logxmin, double invLDBin) {
   const double xv = Max(G4H_LD(data), Min(G4H_LD(data + 3 * (ndata - 1)), x));
   const int idx   = LogBin(logx, logxmin, invLDBin, ndata);
   const int idx3  = 3 * idx;
   return Spline(G4H_LD(data + idx3), G4H_LD(data + idx3 + 3), G4H_LD(data + idx3 + 1), G4H_LD(data + idx3 + 4),
                 G4H_LD(data + idx3 + 2), G4H_LD(data + idx3 + 5), xv);
+}
+
+G4H_LEAF double SplineLogXYSD(int ndata, const double* data, double x, double logx, double logxmin, double invLDBin) {
+  return SplineLogXYSDInl(ndata, data, x, logx, logxmin, invLDBin);
 }
 
 // ---- e-/e+ accessors, G4HepEmElectronManager.icc:486-599 -----------------------------------------

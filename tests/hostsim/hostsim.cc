@@ -8,6 +8,7 @@
 #include <vector>
 
 #include "../../g4hepem_b200/csrc/g4h_batch_io.cuh"
+#include "../../g4hepem_b200/csrc/g4h_stages.cuh"
 #include "../../g4hepem_b200/csrc/g4h_view.cuh"
 
 using namespace g4h;
@@ -119,6 +120,14 @@ int g4hsim_electron(const G4HB200Tables* t, G4HB200ElectronBatch* b, G4HB200Seco
     StoreElectron(*b, i, s, rng);
     if (b->mfp01 != nullptr) StoreElectronHandOver(*b, i, s);
   }
+  return 0;
+}
+
+// the staged HowFar (g4h_stages.cuh), stage after stage over the whole batch like the kernels do
+int g4hsim_electron_howfar_staged(const G4HB200Tables* t, G4HB200ElectronBatch* b, uint64_t seed) {
+  const TablesView tv = MakeView(*t);
+  for (int64_t i = 0; i < b->n; ++i) StageHowFarXS(tv, *b, i, seed);
+  for (int64_t i = 0; i < b->n; ++i) StageHowFarMSC<true>(tv, *b, i, seed);
   return 0;
 }
 

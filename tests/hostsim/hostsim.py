@@ -73,6 +73,10 @@ class HostSim:
     def electron_howfar(self, b, seed):
         self._run(self.lib.g4hsim_electron, b, None, seed, 0)
 
+    def electron_howfar_staged(self, b, seed):
+        s = b.as_struct()
+        self.lib.g4hsim_electron_howfar_staged(self.t, C.byref(s), C.c_uint64(seed))
+
     def electron_perform(self, b, sec, seed):
         self._run(self.lib.g4hsim_electron, b, sec, seed, 1)
 

@@ -34,7 +34,8 @@ def test_vdt_and_lookups_bit_exact(sim, reference, flat_tables):
     assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
 
 
-def test_electron_multi_step_with_geometry_stub(sim, reference, flat_tables):
+@pytest.mark.parametrize("staged", [False, True])
+def test_electron_multi_step_with_geometry_stub(sim, reference, flat_tables, staged):
     n = 20000
     a = batches.make_electron_batch(n, flat_tables.num_matcut, seed=5)
     b = a.copy()
@@ -42,8 +43,9 @@ def test_electron_multi_step_with_geometry_stub(sim, reference, flat_tables):
     for _ in range(4):
         qa, qb = batches.SecondaryHostQueue(2 * n), batches.SecondaryHostQueue(2 * n)
         reference.electron_howfar(a, 2026, 4)
-        sim.electron_howfar(b, 2026)
-        assert compare.total_bad(compare.compare_electron_batches(a, b)) == 0
+        (sim.electron_howfar_staged if staged else sim.electron_howfar)(b, 2026)
+        rep = compare.compare_electron_batches(a, b)
+        assert compare.total_bad(rep) == 0, compare.format_report(rep, True)
         cut = rng.uniform(size=n) < 0.2
         f = rng.uniform(0.3, 1.0, n)
         for x in (a, b):

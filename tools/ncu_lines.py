@@ -12,7 +12,7 @@ import sys
 import tempfile
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-lib = os.path.join(ROOT, "g4hepem_b200", "csrc", "libg4hepem_b200.so")
+lib = os.environ.get("G4HB200_LIB") or os.path.join(ROOT, "g4hepem_b200", "csrc", "libg4hepem_b200.so")
 rep, pat = sys.argv[1], sys.argv[2]
 which = int(sys.argv[3]) if len(sys.argv) > 3 else 0
 top = int(sys.argv[4]) if len(sys.argv) > 4 else 40

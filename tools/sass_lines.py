@@ -9,7 +9,7 @@ import sys
 import tempfile
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-lib = os.path.join(ROOT, "g4hepem_b200", "csrc", "libg4hepem_b200.so")
+lib = os.environ.get("G4HB200_LIB") or os.path.join(ROOT, "g4hepem_b200", "csrc", "libg4hepem_b200.so")
 pat = sys.argv[1]
 top = int(sys.argv[2]) if len(sys.argv) > 2 else 30
 tmp = tempfile.mkdtemp()

@@ -45,7 +45,8 @@ SEC_BYTES = 16 + 16 + 8 + 8        # one secondary record
 STAGE_BYTES = {
     # (bytes read, bytes written, secondaries) per track a stage processes; 16 B per {a,b} group, 16 B meta, 4 B winner
     "ElHowFarXSKernel": (3 * 16 + 16, 7 * 16 + 16 + 4, 0),
-    "ElHowFarMSCKernel": (6 * 16 + 16 + 4, 6 * 16 + 16 + 4, 0),
+    "ElHowFarMSCKernel": (7 * 16 + 16 + 4, 8 * 16 + 16 + 4, 0),
+    "ElHowFarMSCRangeKernel": (4 + 3 * 16 + 16 + 4, 4 * 16 + 4, 0),
     "ElContinuousKernel": (7 * 16 + 16 + 9 * 16 + 4, 10 * 16 + 16 + 4 + 16 + 16, 0),
     "ElFluctuationKernel": (4 + 16 + 3 * 16 + 4, 3 * 16 + 16, 0),
     "ElDiscreteKernel": (4 + 16 + 16 + 4 + 16 + 16, 3 * 16, 0),

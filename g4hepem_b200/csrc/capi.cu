@@ -8,6 +8,7 @@
 #include <cstring>
 #include <new>
 #include <string>
+#include <unordered_map>
 #include <vector>
 
 #include "../../include/g4hepem_b200.h"
@@ -108,6 +109,11 @@ struct G4HB200 {
     int64_t cap = 0;
     cudaStream_t stream = nullptr;   // chunk stream of the host entry points
     cudaEvent_t counted = nullptr;   // the chunk's secondary count has landed in pinnedCount
+    // the final-state samplers work on disjoint queues: they run side by side on these streams (fork / join)
+    static constexpr int kNumAux = 5;
+    cudaStream_t aux[kNumAux] = {};
+    cudaEvent_t fork = nullptr;
+    cudaEvent_t join[kNumAux] = {};
   };
   static constexpr int kNumSlots = 4;
   WorkSlot slots[kNumSlots];         // slot 0 also serves the device-batch entry points
@@ -125,9 +131,25 @@ struct G4HB200 {
     int64_t n;
   };
   std::vector<TimedCall> timed;
+  std::unordered_map<const void*, int> residentCtas;  // per kernel: CTAs of kThreadsPerBlock threads that fit on one SM
 };
 
 namespace {
+
+// One wave: as many CTAs as are resident at once (SM count x occupancy of that kernel), never more than the
+// work needs.  Every kernel here is a grid-stride loop, and a CTA costs ~2.5 us of launch + first-load latency
+// whatever it does: with the former 8 CTAs per SM a queue kernel over a thousand tracks took 11 us.
+template <class K>
+int OneWave(G4HB200* h, K kernel, int64_t n) {
+  const void* key = reinterpret_cast<const void*>(kernel);
+  auto it = h->residentCtas.find(key);
+  if (it == h->residentCtas.end()) {
+    int perSM = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, kernel, kThreadsPerBlock, 0) != cudaSuccess || perSM < 1) perSM = 1;
+    it = h->residentCtas.emplace(key, perSM).first;
+  }
+  return GridFor(n, h->smCount, it->second);
+}
 
 template <class T>
 int DevAlloc(T*& p, size_t count) {
@@ -222,7 +244,7 @@ int LaunchElectron(G4HB200* h, G4HB200ElectronBatch* dev, G4HB200SecondaryQueue*
   if (kMode != 0 && sec == nullptr) return Fail(G4HB200_EINVAL, "secondary queue required");
   if (dev->n == 0) return 0;
   const G4HB200SecondaryQueue q = sec != nullptr ? *sec : NullQueue();
-  const int grid = GridFor(dev->n, h->smCount, 8);
+  const int grid = OneWave(h, ElectronKernel<kMode>, dev->n);
   ElectronKernel<kMode><<<grid, kThreadsPerBlock, 0, static_cast<cudaStream_t>(stream)>>>(h->view, *dev, q, seed);
   ++h->launches;
   G4H_CUDA(cudaGetLastError());
@@ -237,7 +259,7 @@ int LaunchGamma(G4HB200* h, G4HB200GammaBatch* dev, G4HB200SecondaryQueue* sec, 
   if (kMode != 0 && sec == nullptr) return Fail(G4HB200_EINVAL, "secondary queue required");
   if (dev->n == 0) return 0;
   const G4HB200SecondaryQueue q = sec != nullptr ? *sec : NullQueue();
-  const int grid = GridFor(dev->n, h->smCount, 8);
+  const int grid = OneWave(h, GammaKernel<kMode>, dev->n);
   GammaKernel<kMode><<<grid, kThreadsPerBlock, 0, static_cast<cudaStream_t>(stream)>>>(h->view, *dev, q, seed);
   ++h->launches;
   G4H_CUDA(cudaGetLastError());
@@ -271,17 +293,17 @@ int EnsureElectronWork(G4HB200::WorkSlot& slot, int64_t n) {
 
 // pipeline stages of the e-/e+ step, in launch order (g4h_pipeline.cuh)
 enum ElStage {
-  kSHowFarXS = 0, kSHowFarMSC, kSContinuous, kSFluct, kSDiscrete, kSMoller, kSBhabha, kSSB, kSRB, kSAnnih, kSAtRest,
+  kSHowFarXS = 0, kSHowFarMSC, kSHowFarMSCRange, kSContinuous, kSFluct, kSDiscrete, kSMoller, kSBhabha, kSSB, kSRB, kSAnnih, kSAtRest,
   kNumElStages
 };
 static_assert(kNumElStages <= G4HB200_NUM_STAGES, "G4HB200_NUM_STAGES too small");
 // pipeline stage -> queue that feeds it (-1: every track of the batch)
-const int kStageQueue[G4HB200_NUM_STAGES] = {-1, -1, -1, kQFluct, kQDiscrete, kQMoller, kQBhabha, kQSB, kQRB, kQAnnih, kQAtRest,
-                                             -1, -1, -1, -1, -1};
+const int kStageQueue[G4HB200_NUM_STAGES] = {-1, -1, kQConvRange, -1, kQFluct, kQDiscrete, kQMoller, kQBhabha, kQSB, kQRB, kQAnnih, kQAtRest,
+                                             -1, -1, -1, -1};
 const char* const kStageName[G4HB200_NUM_STAGES] = {
-    "ElHowFarXSKernel", "ElHowFarMSCKernel", "ElContinuousKernel", "ElFluctuationKernel", "ElDiscreteKernel",
+    "ElHowFarXSKernel", "ElHowFarMSCKernel", "ElHowFarMSCRangeKernel", "ElContinuousKernel", "ElFluctuationKernel", "ElDiscreteKernel",
     "ElSamplerKernel<Moller>", "ElSamplerKernel<Bhabha>", "ElSamplerKernel<SeltzerBerger>", "ElSamplerKernel<RelBrem>",
-    "ElSamplerKernel<Annihilation>", "ElSamplerKernel<AtRest>", "", "", "", "", ""};
+    "ElSamplerKernel<Annihilation>", "ElSamplerKernel<AtRest>", "", "", "", ""};
 
 struct StageTimer {
   G4HB200* h;
@@ -306,25 +328,31 @@ struct StageTimer {
     return cudaSuccess;
   }
   // bracket one launch: Before(stage) ... kernel ... After(stage)
-  cudaError_t Before(int stage) { return tc != nullptr ? cudaEventRecord(tc->ev[2 * stage], st) : cudaSuccess; }
-  cudaError_t After(int stage) {
+  cudaError_t Before(int stage) { return Before(stage, st); }
+  cudaError_t After(int stage) { return After(stage, st); }
+  cudaError_t Before(int stage, cudaStream_t on) { return tc != nullptr ? cudaEventRecord(tc->ev[2 * stage], on) : cudaSuccess; }
+  cudaError_t After(int stage, cudaStream_t on) {
     ++h->launches;
     if (tc == nullptr) return cudaGetLastError();
     tc->ran[stage] = true;
-    return cudaEventRecord(tc->ev[2 * stage + 1], st);
+    return cudaEventRecord(tc->ev[2 * stage + 1], on);
   }
 };
 
 // G4HepEmElectronManager::HowFar as two kernels (g4h_stages.cuh)
 template <bool kStoreResults>
-int LaunchHowFarStages(G4HB200* h, G4HB200ElectronBatch* dev, uint64_t seed, cudaStream_t st, StageTimer& t) {
-  const int grid = GridFor(dev->n, h->smCount, 8);
+int LaunchHowFarStages(G4HB200* h, G4HB200ElectronBatch* dev, const ElectronWork& w, uint64_t seed, cudaStream_t st,
+                       StageTimer& t) {
+  const int64_t n = dev->n;
   G4H_CUDA(t.Before(kSHowFarXS));
-  ElHowFarXSKernel<<<grid, kThreadsPerBlock, 0, st>>>(h->view, *dev, seed);
+  ElHowFarXSKernel<<<OneWave(h, ElHowFarXSKernel, n), kThreadsPerBlock, 0, st>>>(h->view, *dev, seed);
   G4H_CUDA(t.After(kSHowFarXS));
   G4H_CUDA(t.Before(kSHowFarMSC));
-  ElHowFarMSCKernel<kStoreResults><<<grid, kThreadsPerBlock, 0, st>>>(h->view, *dev, seed);
+  ElHowFarMSCKernel<kStoreResults><<<OneWave(h, ElHowFarMSCKernel<kStoreResults>, n), kThreadsPerBlock, 0, st>>>(h->view, *dev, w, seed);
   G4H_CUDA(t.After(kSHowFarMSC));
+  G4H_CUDA(t.Before(kSHowFarMSCRange));
+  ElHowFarMSCRangeKernel<<<OneWave(h, ElHowFarMSCRangeKernel, n), kThreadsPerBlock, 0, st>>>(h->view, *dev, w);
+  G4H_CUDA(t.After(kSHowFarMSCRange));
   return 0;
 }
 
@@ -333,8 +361,12 @@ int LaunchElectronHowFar(G4HB200* h, G4HB200ElectronBatch* dev, uint64_t seed, v
   if (rc != 0) return rc;
   if (dev == nullptr || dev->n < 0) return Fail(G4HB200_EINVAL, "bad electron batch");
   if (dev->n == 0) return 0;
+  if (dev->n > 0x7fffffff) return Fail(G4HB200_EINVAL, "batch too large (track indices are 32 bit)");
+  if ((rc = EnsureElectronWork(h->slots[0], dev->n)) != 0) return rc;
+  const ElectronWork& w = h->slots[0].work;
   StageTimer t{h, static_cast<cudaStream_t>(stream)};
-  rc = LaunchHowFarStages<true>(h, dev, seed, t.st, t);
+  G4H_CUDA(cudaMemsetAsync(w.count, 0, kNumElQueues * sizeof(int32_t), t.st));
+  rc = LaunchHowFarStages<true>(h, dev, w, seed, t.st, t);
   if (rc != 0) return rc;
   G4H_CUDA(cudaGetLastError());
   return 0;
@@ -352,25 +384,45 @@ int LaunchElectronPipeline(G4HB200* h, G4HB200ElectronBatch* dev, G4HB200Seconda
   if (dev->n > 0x7fffffff) return Fail(G4HB200_EINVAL, "batch too large (track indices are 32 bit)");
   if ((rc = EnsureElectronWork(h->slots[slotIndex], dev->n)) != 0) return rc;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  const int grid = GridFor(dev->n, h->smCount, 8);
+  const int64_t n = dev->n;
   const ElectronWork& w = h->slots[slotIndex].work;
   G4H_CUDA(cudaMemsetAsync(w.count, 0, kNumElQueues * sizeof(int32_t), st));
   StageTimer t{h, st};
   G4H_CUDA(t.Begin(dev->n));
-  if (kFused && (rc = LaunchHowFarStages<true>(h, dev, seed, st, t)) != 0) return rc;
+  if (kFused && (rc = LaunchHowFarStages<true>(h, dev, w, seed, st, t)) != 0) return rc;
 #define G4H_STAGE(stage, ...)       \
   G4H_CUDA(t.Before(stage));        \
   __VA_ARGS__;                      \
   G4H_CUDA(t.After(stage))
-  G4H_STAGE(kSContinuous, ElContinuousKernel<<<grid, kThreadsPerBlock, 0, st>>>(h->view, *dev, w, seed));
-  G4H_STAGE(kSFluct, ElFluctuationKernel<<<grid, kThreadsPerBlock, 0, st>>>(h->view, *dev, w, seed));
-  G4H_STAGE(kSDiscrete, ElDiscreteKernel<<<grid, kThreadsPerBlock, 0, st>>>(h->view, *dev, w, seed));
-  G4H_STAGE(kSMoller, ElSamplerKernel<kQMoller><<<grid, kThreadsPerBlock, 0, st>>>(h->view, *dev, w, *sec, seed));
-  G4H_STAGE(kSBhabha, ElSamplerKernel<kQBhabha><<<grid, kThreadsPerBlock, 0, st>>>(h->view, *dev, w, *sec, seed));
-  G4H_STAGE(kSSB, ElSamplerKernel<kQSB><<<grid, kThreadsPerBlock, 0, st>>>(h->view, *dev, w, *sec, seed));
-  G4H_STAGE(kSRB, ElSamplerKernel<kQRB><<<grid, kThreadsPerBlock, 0, st>>>(h->view, *dev, w, *sec, seed));
-  G4H_STAGE(kSAnnih, ElSamplerKernel<kQAnnih><<<grid, kThreadsPerBlock, 0, st>>>(h->view, *dev, w, *sec, seed));
-  G4H_STAGE(kSAtRest, ElSamplerKernel<kQAtRest><<<grid, kThreadsPerBlock, 0, st>>>(h->view, *dev, w, *sec, seed));
+  G4H_STAGE(kSContinuous, ElContinuousKernel<<<OneWave(h, ElContinuousKernel, n), kThreadsPerBlock, 0, st>>>(h->view, *dev, w, seed));
+  G4H_STAGE(kSFluct, ElFluctuationKernel<<<OneWave(h, ElFluctuationKernel, n), kThreadsPerBlock, 0, st>>>(h->view, *dev, w, seed));
+  G4H_STAGE(kSDiscrete, ElDiscreteKernel<<<OneWave(h, ElDiscreteKernel, n), kThreadsPerBlock, 0, st>>>(h->view, *dev, w, seed));
+#undef G4H_STAGE
+  // fork: the six samplers read disjoint queues and write disjoint tracks (+ atomic appends of secondaries)
+  G4HB200::WorkSlot& slot = h->slots[slotIndex];
+  if (slot.fork == nullptr) {
+    G4H_CUDA(cudaEventCreateWithFlags(&slot.fork, cudaEventDisableTiming));
+    for (int k = 0; k < G4HB200::WorkSlot::kNumAux; ++k) {
+      G4H_CUDA(cudaStreamCreateWithFlags(&slot.aux[k], cudaStreamNonBlocking));
+      G4H_CUDA(cudaEventCreateWithFlags(&slot.join[k], cudaEventDisableTiming));
+    }
+  }
+  G4H_CUDA(cudaEventRecord(slot.fork, st));
+  for (int k = 0; k < G4HB200::WorkSlot::kNumAux; ++k) G4H_CUDA(cudaStreamWaitEvent(slot.aux[k], slot.fork, 0));
+#define G4H_STAGE(stage, on, ...)   \
+  G4H_CUDA(t.Before(stage, on));    \
+  __VA_ARGS__;                      \
+  G4H_CUDA(t.After(stage, on))
+  G4H_STAGE(kSRB, st, ElSamplerKernel<kQRB><<<OneWave(h, ElSamplerKernel<kQRB>, n), kThreadsPerBlock, 0, st>>>(h->view, *dev, w, *sec, seed));
+  G4H_STAGE(kSSB, slot.aux[0], ElSamplerKernel<kQSB><<<OneWave(h, ElSamplerKernel<kQSB>, n), kThreadsPerBlock, 0, slot.aux[0]>>>(h->view, *dev, w, *sec, seed));
+  G4H_STAGE(kSBhabha, slot.aux[1], ElSamplerKernel<kQBhabha><<<OneWave(h, ElSamplerKernel<kQBhabha>, n), kThreadsPerBlock, 0, slot.aux[1]>>>(h->view, *dev, w, *sec, seed));
+  G4H_STAGE(kSMoller, slot.aux[2], ElSamplerKernel<kQMoller><<<OneWave(h, ElSamplerKernel<kQMoller>, n), kThreadsPerBlock, 0, slot.aux[2]>>>(h->view, *dev, w, *sec, seed));
+  G4H_STAGE(kSAnnih, slot.aux[3], ElSamplerKernel<kQAnnih><<<OneWave(h, ElSamplerKernel<kQAnnih>, n), kThreadsPerBlock, 0, slot.aux[3]>>>(h->view, *dev, w, *sec, seed));
+  G4H_STAGE(kSAtRest, slot.aux[4], ElSamplerKernel<kQAtRest><<<OneWave(h, ElSamplerKernel<kQAtRest>, n), kThreadsPerBlock, 0, slot.aux[4]>>>(h->view, *dev, w, *sec, seed));
+  for (int k = 0; k < G4HB200::WorkSlot::kNumAux; ++k) {
+    G4H_CUDA(cudaEventRecord(slot.join[k], slot.aux[k]));
+    G4H_CUDA(cudaStreamWaitEvent(st, slot.join[k], 0));
+  }
 #undef G4H_STAGE
   if (t.tc != nullptr) {
     G4H_CUDA(cudaMemcpyAsync(t.tc->counts, w.count, kNumElQueues * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
@@ -493,6 +545,9 @@ int g4hb200_destroy(G4HB200* h) {
     if (slot.mem != nullptr) cudaFree(slot.mem);
     if (slot.stream != nullptr) cudaStreamDestroy(slot.stream);
     if (slot.counted != nullptr) cudaEventDestroy(slot.counted);
+    for (auto& a : slot.aux) if (a != nullptr) cudaStreamDestroy(a);
+    for (auto& e : slot.join) if (e != nullptr) cudaEventDestroy(e);
+    if (slot.fork != nullptr) cudaEventDestroy(slot.fork);
   }
   if (h->pinnedCounts != nullptr) cudaFreeHost(h->pinnedCounts);
   if (h->chunkCounters != nullptr) cudaFree(h->chunkCounters);
@@ -663,7 +718,7 @@ int g4hb200_electron_lookups(G4HB200* h, int64_t n, const int32_t* imc, const do
   if (rc != 0) return rc;
   if (n < 0 || (n > 0 && (!imc || !ekin || !logekin || !out))) return Fail(G4HB200_EINVAL, "bad argument");
   if (n == 0) return 0;
-  ElectronLookupsKernel<<<GridFor(n, h->smCount, 8), kThreadsPerBlock, 0, static_cast<cudaStream_t>(stream)>>>(
+  ElectronLookupsKernel<<<OneWave(h, ElectronLookupsKernel, n), kThreadsPerBlock, 0, static_cast<cudaStream_t>(stream)>>>(
       h->view, n, imc, ekin, logekin, is_electron ? 0 : 1, out);
   ++h->launches;
   G4H_CUDA(cudaGetLastError());
@@ -676,7 +731,7 @@ int g4hb200_electron_stepping_xsecs(G4HB200* h, int64_t n, const int32_t* imc, c
   if (rc != 0) return rc;
   if (n < 0 || (n > 0 && (!imc || !ekin || !logekin || !out))) return Fail(G4HB200_EINVAL, "bad argument");
   if (n == 0) return 0;
-  ElectronSteppingXSecsKernel<<<GridFor(n, h->smCount, 8), kThreadsPerBlock, 0, static_cast<cudaStream_t>(stream)>>>(
+  ElectronSteppingXSecsKernel<<<OneWave(h, ElectronSteppingXSecsKernel, n), kThreadsPerBlock, 0, static_cast<cudaStream_t>(stream)>>>(
       h->view, n, imc, ekin, logekin, is_electron ? 0 : 1, out);
   ++h->launches;
   G4H_CUDA(cudaGetLastError());
@@ -689,7 +744,7 @@ int g4hb200_gamma_lookups(G4HB200* h, int64_t n, const int32_t* imc, const doubl
   if (rc != 0) return rc;
   if (n < 0 || (n > 0 && (!imc || !ekin || !logekin || !urnd || !out_mxsec || !out_pid))) return Fail(G4HB200_EINVAL, "bad argument");
   if (n == 0) return 0;
-  GammaLookupsKernel<<<GridFor(n, h->smCount, 8), kThreadsPerBlock, 0, static_cast<cudaStream_t>(stream)>>>(
+  GammaLookupsKernel<<<OneWave(h, GammaLookupsKernel, n), kThreadsPerBlock, 0, static_cast<cudaStream_t>(stream)>>>(
       h->view, n, imc, ekin, logekin, urnd, out_mxsec, out_pid);
   ++h->launches;
   G4H_CUDA(cudaGetLastError());
@@ -704,7 +759,7 @@ int g4hb200_select_target_element(G4HB200* h, int kind, int is_electron, int64_t
   if (kind < 0 || kind > 2 || n < 0 || (n > 0 && (!imc || !ekin || !logekin || !urnd || !out_elem)))
     return Fail(G4HB200_EINVAL, "bad argument");
   if (n == 0) return 0;
-  SelectTargetElementKernel<<<GridFor(n, h->smCount, 8), kThreadsPerBlock, 0, static_cast<cudaStream_t>(stream)>>>(
+  SelectTargetElementKernel<<<OneWave(h, SelectTargetElementKernel, n), kThreadsPerBlock, 0, static_cast<cudaStream_t>(stream)>>>(
       h->view, kind, is_electron ? 0 : 1, n, imc, ekin, logekin, urnd, out_elem);
   ++h->launches;
   G4H_CUDA(cudaGetLastError());
@@ -716,7 +771,7 @@ int g4hb200_vdt_log_exp(G4HB200* h, int64_t n, const double* x, double* out_log,
   if (rc != 0) return rc;
   if (n < 0 || (n > 0 && (!x || !out_log || !out_exp))) return Fail(G4HB200_EINVAL, "bad argument");
   if (n == 0) return 0;
-  VdtLogExpKernel<<<GridFor(n, h->smCount, 8), kThreadsPerBlock, 0, static_cast<cudaStream_t>(stream)>>>(n, x, out_log, out_exp);
+  VdtLogExpKernel<<<OneWave(h, VdtLogExpKernel, n), kThreadsPerBlock, 0, static_cast<cudaStream_t>(stream)>>>(n, x, out_log, out_exp);
   ++h->launches;
   G4H_CUDA(cudaGetLastError());
   return 0;
@@ -728,7 +783,7 @@ int g4hb200_rng_uniforms(G4HB200* h, uint64_t seed, int64_t n, const int32_t* tr
   if (rc != 0) return rc;
   if (n < 0 || ndraw < 0 || (n > 0 && (!track_id || !out))) return Fail(G4HB200_EINVAL, "bad argument");
   if (n == 0 || ndraw == 0) return 0;
-  RngUniformsKernel<<<GridFor(n, h->smCount, 8), kThreadsPerBlock, 0, static_cast<cudaStream_t>(stream)>>>(seed, n, track_id, ndraw, out);
+  RngUniformsKernel<<<OneWave(h, RngUniformsKernel, n), kThreadsPerBlock, 0, static_cast<cudaStream_t>(stream)>>>(seed, n, track_id, ndraw, out);
   ++h->launches;
   G4H_CUDA(cudaGetLastError());
   return 0;

@@ -14,7 +14,8 @@ struct Pair {
 
 G4H_FN Pair LoadPair(const double* group, int64_t i) {
 #if defined(__CUDA_ARCH__)
-  const double2 v = reinterpret_cast<const double2*>(group)[i];
+  // track state streams through once per kernel: evict-first keeps the tables in L1/L2
+  const double2 v = __ldcs(reinterpret_cast<const double2*>(group) + i);
   return Pair{v.x, v.y};
 #else
   return Pair{group[2 * i], group[2 * i + 1]};
@@ -23,7 +24,7 @@ G4H_FN Pair LoadPair(const double* group, int64_t i) {
 
 G4H_FN void StorePair(double* group, int64_t i, double a, double b) {
 #if defined(__CUDA_ARCH__)
-  reinterpret_cast<double2*>(group)[i] = make_double2(a, b);
+  __stcs(reinterpret_cast<double2*>(group) + i, make_double2(a, b));
 #else
   group[2 * i]     = a;
   group[2 * i + 1] = b;
@@ -36,7 +37,7 @@ struct Meta {
 
 G4H_FN Meta LoadMeta(const int32_t* meta, int64_t i) {
 #if defined(__CUDA_ARCH__)
-  const int4 v = reinterpret_cast<const int4*>(meta)[i];
+  const int4 v = __ldcs(reinterpret_cast<const int4*>(meta) + i);
   return Meta{v.x, v.y, v.z, v.w};
 #else
   return Meta{meta[4 * i], meta[4 * i + 1], meta[4 * i + 2], meta[4 * i + 3]};
@@ -45,7 +46,7 @@ G4H_FN Meta LoadMeta(const int32_t* meta, int64_t i) {
 
 G4H_FN void StoreMeta(int32_t* meta, int64_t i, const Meta& m) {
 #if defined(__CUDA_ARCH__)
-  reinterpret_cast<int4*>(meta)[i] = make_int4(m.imc, m.flags, m.id, m.draw);
+  __stcs(reinterpret_cast<int4*>(meta) + i, make_int4(m.imc, m.flags, m.id, m.draw));
 #else
   meta[4 * i] = m.imc; meta[4 * i + 1] = m.flags; meta[4 * i + 2] = m.id; meta[4 * i + 3] = m.draw;
 #endif

@@ -23,7 +23,7 @@ constexpr int kThreadsPerBlock = 256;
 #define G4H_MINB_CONT 2
 #endif
 #ifndef G4H_MINB_QUEUE
-#define G4H_MINB_QUEUE 2
+#define G4H_MINB_QUEUE 3
 #endif
 
 // ---- CTA aggregated appends ----------------------------------------------------------------------------------

@@ -24,7 +24,7 @@
 
 namespace g4h {
 
-enum ElQueue { kQFluct = 0, kQDiscrete, kQAtRest, kQMoller, kQBhabha, kQSB, kQRB, kQAnnih, kNumElQueues };
+enum ElQueue { kQFluct = 0, kQDiscrete, kQAtRest, kQMoller, kQBhabha, kQSB, kQRB, kQAnnih, kQConvRange, kNumElQueues };
 
 struct ElectronWork {
   double* prestep;                // [n] pairs {preStepEkin, preStepLogEkin}
@@ -37,7 +37,7 @@ struct ElectronWork {
 #define G4H_MINB_XS 3
 #endif
 #ifndef G4H_MINB_MSCLIM
-#define G4H_MINB_MSCLIM 3
+#define G4H_MINB_MSCLIM 4
 #endif
 __global__ void __launch_bounds__(kThreadsPerBlock, G4H_MINB_XS)
 ElHowFarXSKernel(const __grid_constant__ TablesView tv, const __grid_constant__ G4HB200ElectronBatch b, uint64_t seed) {
@@ -49,10 +49,25 @@ ElHowFarXSKernel(const __grid_constant__ TablesView tv, const __grid_constant__ 
 
 template <bool kStoreResults>
 __global__ void __launch_bounds__(kThreadsPerBlock, G4H_MINB_MSCLIM)
-ElHowFarMSCKernel(const __grid_constant__ TablesView tv, const __grid_constant__ G4HB200ElectronBatch b, uint64_t seed) {
+ElHowFarMSCKernel(const __grid_constant__ TablesView tv, const __grid_constant__ G4HB200ElectronBatch b,
+                  const __grid_constant__ ElectronWork w, uint64_t seed) {
   const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
-  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < b.n; i += stride) {
-    StageHowFarMSC<kStoreResults>(tv, b, i, seed);
+  const int64_t nRound = RoundUpToCta(b.n);
+  __shared__ CtaCounters<1> cc;
+  cc.Init();
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < nRound; i += stride) {
+    const bool queued = i < b.n && StageHowFarMSC<kStoreResults>(tv, b, i, seed);
+    RouteToQueues<1>(cc, queued ? 0 : -1, static_cast<int32_t>(i), w.queue + kQConvRange, w.count + kQConvRange);
+  }
+}
+
+__global__ void __launch_bounds__(kThreadsPerBlock, G4H_MINB_QUEUE)
+ElHowFarMSCRangeKernel(const __grid_constant__ TablesView tv, const __grid_constant__ G4HB200ElectronBatch b,
+                       const __grid_constant__ ElectronWork w) {
+  const int cnt = w.count[kQConvRange];
+  const int stride = gridDim.x * blockDim.x;
+  for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < cnt; q += stride) {
+    StageHowFarMSCRange(tv, b, w.queue[kQConvRange][q]);
   }
 }
 

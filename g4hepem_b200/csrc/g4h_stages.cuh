@@ -93,7 +93,8 @@ G4H_FN double HowFarToDiscreteInteractionILP(const TablesView& tv, ElectronState
   const double* rp    = tv.regionPars + 8 * G4H_LD(tv.mcIreg + theIMC);
   const double frange = G4H_LD(rp + kRFinalRange);
   const double drange = G4H_LD(rp + kRDRoverRange);
-  double pStepLength = (range > frange) ? range * drange + frange * (1.0 - drange) * (2.0 - frange / range) : range;
+  // FastDiv: the quotient is only used when range > frange > 0, sigma > 0, sigma_tr1 > 0 (selected below)
+  double pStepLength = (range > frange) ? range * drange + frange * (1.0 - drange) * (2.0 - FastDiv(frange, range)) : range;
   // restricted ioni / brem: per couple header {numIoni, ...}; brem follows the 3*numIoni + 5 ioni entries
   const int iIoni   = G4H_LD(ed.resStart + theIMC);
   const int numIoni = static_cast<int>(G4H_LD(ed.resData + iIoni));
@@ -111,7 +112,7 @@ G4H_FN double HowFarToDiscreteInteractionILP(const TablesView& tv, ElectronState
 #pragma unroll
   for (int ip = 0; ip < 4; ++ip) {
     const double mxsec = mxSecs[ip];
-    const double mfp   = (mxsec > 0.) ? 1. / mxsec : kALargeValue;
+    const double mfp   = (mxsec > 0.) ? FastDiv(1., mxsec) : kALargeValue;
     s.mfp[ip] = mfp;
     const double dStepLimit = mfp * s.nIA[ip];
     if (dStepLimit < pStepLength) {
@@ -122,7 +123,7 @@ G4H_FN double HowFarToDiscreteInteractionILP(const TablesView& tv, ElectronState
   s.pStep  = pStepLength;
   s.winner = indxWinnerProcess;
   s.gStep  = pStepLength;
-  return tr1 > 0. ? 1. / tr1 : kALargeValue;  // GetTransportMFP (.icc:576-582)
+  return tr1 > 0. ? FastDiv(1., tr1) : kALargeValue;  // GetTransportMFP (.icc:576-582)
 }
 
 // the condition under which HowFarToMSC evaluates anything (.icc:131-132)
@@ -160,13 +161,35 @@ G4H_FN void StageHowFarXS(const TablesView& tv, const G4HB200ElectronBatch& b, i
 }
 
 // ---- HowFar, part 2 -----------------------------------------------------------------------------------------
+// the end of HowFarToMSC (.icc:155-163) once zPath is known
+G4H_FN void FinishHowFarMSC(const G4HB200ElectronBatch& b, int64_t i, const ElectronState& s, double pStepLength, int winner) {
+  if (s.trueStep < pStepLength) {
+    winner      = -2;
+    pStepLength = s.trueStep;
+  }
+  const double gStep = Min(s.zPath, pStepLength);
+  StorePair(b.tstep_zpath, i, s.trueStep, s.zPath);
+  StorePair(b.par12, i, s.par1, s.par2);
+  StorePair(b.par3_pad, i, s.par3, 0.0);
+  StorePair(b.gstep_pstep, i, gStep, pStepLength);
+  b.winner[i] = winner;
+}
+
+// returns true when the true -> geometrical conversion needs the inverse range regime: the track then goes to the
+// kQConvRange queue and StageHowFarMSCRange finishes it
 template <bool kStoreResults>
-G4H_FN void StageHowFarMSC(const TablesView& tv, const G4HB200ElectronBatch& b, int64_t i, uint64_t seed) {
+G4H_FN bool StageHowFarMSC(const TablesView& tv, const G4HB200ElectronBatch& b, int64_t i, uint64_t seed) {
   const Meta m  = LoadMeta(b.meta, i);
   const Pair e  = LoadPair(b.ekin_logekin, i);
   const Pair gp = LoadPair(b.gstep_pstep, i);
   uint32_t f = static_cast<uint32_t>(m.flags);
-  double pStepLength = gp.b;
+  const double pStepLength = gp.b;
+  if (kStoreResults) {
+    // fDisplacement = 0 (.icc:127-129); the energy deposit is not a HowFar field
+    const Pair ed = LoadPair(b.edep_dispx, i);
+    StorePair(b.edep_dispx, i, ed.a, 0.0);
+    StorePair(b.dispy_dispz, i, 0.0, 0.0);
+  }
   if (!MSCStepLimitApplies(pStepLength, e.a)) {
     // HowFarToMSC (.icc:117-130): true = z = physical step, MSC inactive, no displacement; the rest keeps its
     // G4HepEmMSCTrackData::ReSet() value
@@ -175,61 +198,65 @@ G4H_FN void StageHowFarMSC(const TablesView& tv, const G4HB200ElectronBatch& b, 
     StorePair(b.par12, i, -1.0, 0.0);
     StorePair(b.par3_pad, i, 0.0, 0.0);
     StoreMeta(b.meta, i, Meta{m.imc, static_cast<int>(f), m.id, m.draw});
-  } else {
-    const Pair rl  = LoadPair(b.range_lambtr1, i);
-    const Pair dzs = LoadPair(b.dirz_safety, i);
-    const Pair ir  = LoadPair(b.msc_irange_dynrf, i);
-    const Pair tg  = LoadPair(b.msc_tlimmin_gauss, i);
-    ElectronState s;
-    s.ekin = e.a; s.logEkin = e.b;
-    s.imc = m.imc; s.id = m.id;
-    s.isPositron   = (f & G4HB200_F_POSITRON) != 0u;
-    s.onBoundary   = (f & G4HB200_F_ON_BOUNDARY) != 0u;
-    s.mscFirstStep = (f & G4HB200_F_MSC_FIRST_STEP) != 0u;
-    s.mscDisplace  = (f & G4HB200_F_MSC_DISPLACE) != 0u;
-    s.mscNoScatter = (f & G4HB200_F_MSC_NO_SCATTER) != 0u;
-    s.safety = dzs.b;
-    s.range = rl.a; s.lambtr1 = rl.b;
-    s.initialRange = ir.a; s.dynRangeFactor = ir.b; s.tlimitMin = tg.a;
-    s.pStep = pStepLength;
-    Rng rng;
-    rng.Init(seed, static_cast<uint32_t>(m.id), static_cast<uint32_t>(m.draw), (f & G4HB200_F_GAUSS_CACHED) != 0u, tg.b);
-    const bool isElectron = !s.isPositron;
-    const int theImat = G4H_LD(tv.mcImat + s.imc);
-    const int theIreg = G4H_LD(tv.mcIreg + s.imc);
-    s.trueStep  = pStepLength;
-    s.zPath     = pStepLength;
-    s.mscActive = true;
-    UMSCStepLimit(tv, s, s.ekin, theImat, theIreg, s.range, s.safety, s.onBoundary, isElectron, rng);
-    ConvertTrueToGeometricLength(tv, s, s.ekin, s.range, s.imc, isElectron);
-    int winner = b.winner[i];
-    if (s.trueStep < pStepLength) {
-      winner      = -2;
-      pStepLength = s.trueStep;
-    }
-    const double gStep = Min(s.zPath, pStepLength);
-    f &= ~(G4HB200_F_MSC_FIRST_STEP | G4HB200_F_MSC_ACTIVE | G4HB200_F_MSC_DISPLACE | G4HB200_F_MSC_NO_SCATTER |
-           G4HB200_F_GAUSS_CACHED);
-    if (s.mscFirstStep) f |= G4HB200_F_MSC_FIRST_STEP;
-    f |= G4HB200_F_MSC_ACTIVE;
-    if (s.mscDisplace) f |= G4HB200_F_MSC_DISPLACE;
-    if (s.mscNoScatter) f |= G4HB200_F_MSC_NO_SCATTER;
-    if (rng.hasGauss) f |= G4HB200_F_GAUSS_CACHED;
-    StorePair(b.msc_irange_dynrf, i, s.initialRange, s.dynRangeFactor);
-    StorePair(b.msc_tlimmin_gauss, i, s.tlimitMin, rng.gauss);
+    return false;
+  }
+  const Pair rl  = LoadPair(b.range_lambtr1, i);
+  const Pair dzs = LoadPair(b.dirz_safety, i);
+  const Pair ir  = LoadPair(b.msc_irange_dynrf, i);
+  const Pair tg  = LoadPair(b.msc_tlimmin_gauss, i);
+  ElectronState s;
+  s.ekin = e.a; s.logEkin = e.b;
+  s.imc = m.imc; s.id = m.id;
+  s.isPositron   = (f & G4HB200_F_POSITRON) != 0u;
+  s.onBoundary   = (f & G4HB200_F_ON_BOUNDARY) != 0u;
+  s.mscFirstStep = (f & G4HB200_F_MSC_FIRST_STEP) != 0u;
+  s.mscDisplace  = (f & G4HB200_F_MSC_DISPLACE) != 0u;
+  s.mscNoScatter = (f & G4HB200_F_MSC_NO_SCATTER) != 0u;
+  s.safety = dzs.b;
+  s.range = rl.a; s.lambtr1 = rl.b;
+  s.initialRange = ir.a; s.dynRangeFactor = ir.b; s.tlimitMin = tg.a;
+  s.pStep = pStepLength;
+  Rng rng;
+  rng.Init(seed, static_cast<uint32_t>(m.id), static_cast<uint32_t>(m.draw), (f & G4HB200_F_GAUSS_CACHED) != 0u, tg.b);
+  const bool isElectron = !s.isPositron;
+  const int theImat = G4H_LD(tv.mcImat + s.imc);
+  const int theIreg = G4H_LD(tv.mcIreg + s.imc);
+  s.trueStep  = pStepLength;
+  s.zPath     = pStepLength;
+  s.mscActive = true;
+  UMSCStepLimit(tv, s, s.ekin, theImat, theIreg, s.range, s.safety, s.onBoundary, isElectron, rng);
+  const bool rangeRegime = ConvertTrueToGeometricLengthHead(s, s.ekin, s.range);
+  f &= ~(G4HB200_F_MSC_FIRST_STEP | G4HB200_F_MSC_ACTIVE | G4HB200_F_MSC_DISPLACE | G4HB200_F_MSC_NO_SCATTER |
+         G4HB200_F_GAUSS_CACHED);
+  if (s.mscFirstStep) f |= G4HB200_F_MSC_FIRST_STEP;
+  f |= G4HB200_F_MSC_ACTIVE;
+  if (s.mscDisplace) f |= G4HB200_F_MSC_DISPLACE;
+  if (s.mscNoScatter) f |= G4HB200_F_MSC_NO_SCATTER;
+  if (rng.hasGauss) f |= G4HB200_F_GAUSS_CACHED;
+  StorePair(b.msc_irange_dynrf, i, s.initialRange, s.dynRangeFactor);
+  StorePair(b.msc_tlimmin_gauss, i, s.tlimitMin, rng.gauss);
+  StoreMeta(b.meta, i, Meta{m.imc, static_cast<int>(f), m.id, static_cast<int>(rng.draw)});
+  if (rangeRegime) {
+    // hand trueStep over (zPath = trueStep for now); gstep_pstep and the winner still hold the discrete limit
     StorePair(b.tstep_zpath, i, s.trueStep, s.zPath);
-    StorePair(b.par12, i, s.par1, s.par2);
-    StorePair(b.par3_pad, i, s.par3, 0.0);
-    StorePair(b.gstep_pstep, i, gStep, pStepLength);
-    StoreMeta(b.meta, i, Meta{m.imc, static_cast<int>(f), m.id, static_cast<int>(rng.draw)});
-    b.winner[i] = winner;
+    return true;
   }
-  if (kStoreResults) {
-    // fDisplacement = 0 (.icc:127-129); the energy deposit is not a HowFar field
-    const Pair ed = LoadPair(b.edep_dispx, i);
-    StorePair(b.edep_dispx, i, ed.a, 0.0);
-    StorePair(b.dispy_dispz, i, 0.0, 0.0);
-  }
+  FinishHowFarMSC(b, i, s, pStepLength, b.winner[i]);
+  return false;
+}
+
+// the inverse-range regime of the true -> geometrical conversion (.icc:636-647) for the tracks queued by StageHowFarMSC
+G4H_FN void StageHowFarMSCRange(const TablesView& tv, const G4HB200ElectronBatch& b, int64_t i) {
+  const Meta m  = LoadMeta(b.meta, i);
+  const Pair gp = LoadPair(b.gstep_pstep, i);
+  const Pair rl = LoadPair(b.range_lambtr1, i);
+  const Pair tz = LoadPair(b.tstep_zpath, i);
+  ElectronState s;
+  s.lambtr1  = rl.b;
+  s.trueStep = tz.a;
+  s.zPath    = tz.b;
+  ConvertTrueToGeometricLengthRangeRegime(tv, s, rl.a, m.imc, (static_cast<uint32_t>(m.flags) & G4HB200_F_POSITRON) == 0u);
+  FinishHowFarMSC(b, i, s, gp.b, b.winner[i]);
 }
 
 }  // namespace g4h

@@ -88,7 +88,7 @@ enum CutPar { kCElCut = 0, kCPosCut, kCGamCut, kCLogGamCut };
 // ---- G4HepEmRunUtils.icc:49-61 ---------------------------------------------------------------
 G4H_FN double Spline(double x1, double x2, double y1, double y2, double sd1, double sd2, double x) {
   const double dl = x2 - x1;
-  const double b  = Max(0., Min(1., (x - x1) / dl));
+  const double b  = Max(0., Min(1., FastDiv(x - x1, dl)));  // dl: spacing of a table grid
   const double os = 0.166666666667;
   const double c0 = (2.0 - b) * sd1;
   const double c1 = (1.0 + b) * sd2;

@@ -55,6 +55,17 @@ def prep_fresh():
 
 
 timed("electron_step (fused)", lambda: eng.ElectronManager.Step(e, dev, sec, SEED), prep_fresh)
+if os.environ.get("PROBE_STAGES"):
+    prep_fresh()
+    torch.cuda.synchronize()
+    e.set_kernel_timing(True)
+    e.kernel_times()
+    eng.ElectronManager.Step(e, dev, sec, SEED)
+    torch.cuda.synchronize()
+    for name, (ms, nl, items) in e.kernel_times().items():
+        if nl:
+            print(f"   stage {name:32s} {ms * 1000:8.1f} us  {items:9d} tracks", flush=True)
+    e.set_kernel_timing(False)
 timed("electron_howfar", lambda: eng.ElectronManager.HowFar(e, dev, SEED), prep_fresh)
 
 

@@ -13,13 +13,18 @@ rep, tag, cmd = sys.argv[1], sys.argv[2], sys.argv[3]
 raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(raw)))
 hdr, units = rows[0], rows[1]
-NAMES = [("ElectronKernel<0>", "ElectronKernel<0> (HowFar)"), ("ElContinuousKernel", "ElContinuousKernel"),
-         ("ElFluctuationKernel", "ElFluctuationKernel"), ("ElDiscreteKernel", "ElDiscreteKernel"),
-         ("ElSamplerKernel<3>", "ElSamplerKernel<Moller>"), ("ElSamplerKernel<4>", "ElSamplerKernel<Bhabha>"),
-         ("ElSamplerKernel<5>", "ElSamplerKernel<SeltzerBerger>"), ("ElSamplerKernel<6>", "ElSamplerKernel<RelBrem>"),
-         ("ElSamplerKernel<7>", "ElSamplerKernel<Annihilation>"), ("ElSamplerKernel<2>", "ElSamplerKernel<AtRest>"),
-         ("ElectronKernel<2>", "ElectronKernel<2> (monolithic step)"), ("GammaKernel<2>", "GammaKernel<2> (monolithic step)"),
-         ("GammaKernel<0>", "GammaKernel<0> (HowFar)")]
+import re
+
+
+def short_name(kn):
+    """'void g4h::ElSamplerKernel<(int)5>(g4h::TablesView, ...)' -> 'ElSamplerKernel<5>'"""
+    m = re.match(r'(?:void )?(?:g4h::)?([A-Za-z0-9_]+)(<[^(]*>)?\(', kn)
+    if not m:
+        return kn[:40]
+    targs = (m.group(2) or '').replace('(int)', '').replace('(bool)', '')
+    return m.group(1) + targs
+
+
 SCALE = {'Mbyte': 1e6, 'Kbyte': 1e3, 'byte': 1, 'Gbyte': 1e9, 'us': 1e-3, 'ms': 1, 'ns': 1e-6, 'msecond': 1, 'usecond': 1e-3, 'nsecond': 1e-6}
 
 
@@ -34,8 +39,8 @@ md = [f"# {tag} -- `ncu --set full` summary", "", f"Command (on the B200 box): `
       "|---|---|---|---|---|---|---|---|---|---|---|---|"]
 for r in rows[2:]:
     kn = r[hdr.index('Kernel Name')]
-    key = next((b for a, b in NAMES if a in kn), None)
-    if key is None or key in out:
+    key = short_name(kn)
+    if key in out:
         continue
     d = dict(ms=col(r, 'gpu__time_duration.sum'),
              dram_bytes_per_launch=col(r, 'dram__bytes_read.sum') + col(r, 'dram__bytes_write.sum'),

@@ -117,6 +117,7 @@ struct G4HB200 {
   };
   static constexpr int kNumSlots = 4;
   WorkSlot slots[kNumSlots];         // slot 0 also serves the device-batch entry points
+  WorkSlot gmSlot;                   // queues of the gamma pipeline
   int32_t* pinnedCounts = nullptr;   // [kMaxChunks] secondary counts of the chunks of a host call
   int32_t* chunkCounters = nullptr;  // device, [kMaxChunks]
   static constexpr int kMaxChunks = 256;
@@ -294,16 +295,18 @@ int EnsureElectronWork(G4HB200::WorkSlot& slot, int64_t n) {
 // pipeline stages of the e-/e+ step, in launch order (g4h_pipeline.cuh)
 enum ElStage {
   kSHowFarXS = 0, kSHowFarMSC, kSHowFarMSCRange, kSContinuous, kSFluct, kSDiscrete, kSMoller, kSBhabha, kSSB, kSRB, kSAnnih, kSAtRest,
+  kSGammaHead, kSGammaConversion, kSGammaCompton, kSGammaPhotoelectric,
   kNumElStages
 };
 static_assert(kNumElStages <= G4HB200_NUM_STAGES, "G4HB200_NUM_STAGES too small");
 // pipeline stage -> queue that feeds it (-1: every track of the batch)
 const int kStageQueue[G4HB200_NUM_STAGES] = {-1, -1, kQConvRange, -1, kQFluct, kQDiscrete, kQMoller, kQBhabha, kQSB, kQRB, kQAnnih, kQAtRest,
-                                             -1, -1, -1, -1};
+                                             -1, kGQConversion, kGQCompton, kGQPhotoelectric};
 const char* const kStageName[G4HB200_NUM_STAGES] = {
     "ElHowFarXSKernel", "ElHowFarMSCKernel", "ElHowFarMSCRangeKernel", "ElContinuousKernel", "ElFluctuationKernel", "ElDiscreteKernel",
     "ElSamplerKernel<Moller>", "ElSamplerKernel<Bhabha>", "ElSamplerKernel<SeltzerBerger>", "ElSamplerKernel<RelBrem>",
-    "ElSamplerKernel<Annihilation>", "ElSamplerKernel<AtRest>", "", "", "", ""};
+    "ElSamplerKernel<Annihilation>", "ElSamplerKernel<AtRest>", "GammaHeadKernel", "GammaInteractKernel<Conversion>",
+    "GammaInteractKernel<Compton>", "GammaInteractKernel<Photoelectric>"};
 
 struct StageTimer {
   G4HB200* h;
@@ -372,6 +375,8 @@ int LaunchElectronHowFar(G4HB200* h, G4HB200ElectronBatch* dev, uint64_t seed, v
   return 0;
 }
 
+int EnsureAuxStreams(G4HB200::WorkSlot& slot);
+
 // G4HepEmElectronManager::Perform as a pipeline (g4h_pipeline.cuh); kFused: HowFar first
 template <bool kFused>
 int LaunchElectronPipeline(G4HB200* h, G4HB200ElectronBatch* dev, G4HB200SecondaryQueue* sec, uint64_t seed, void* stream,
@@ -400,13 +405,7 @@ int LaunchElectronPipeline(G4HB200* h, G4HB200ElectronBatch* dev, G4HB200Seconda
 #undef G4H_STAGE
   // fork: the six samplers read disjoint queues and write disjoint tracks (+ atomic appends of secondaries)
   G4HB200::WorkSlot& slot = h->slots[slotIndex];
-  if (slot.fork == nullptr) {
-    G4H_CUDA(cudaEventCreateWithFlags(&slot.fork, cudaEventDisableTiming));
-    for (int k = 0; k < G4HB200::WorkSlot::kNumAux; ++k) {
-      G4H_CUDA(cudaStreamCreateWithFlags(&slot.aux[k], cudaStreamNonBlocking));
-      G4H_CUDA(cudaEventCreateWithFlags(&slot.join[k], cudaEventDisableTiming));
-    }
-  }
+  if ((rc = EnsureAuxStreams(slot)) != 0) return rc;
   G4H_CUDA(cudaEventRecord(slot.fork, st));
   for (int k = 0; k < G4HB200::WorkSlot::kNumAux; ++k) G4H_CUDA(cudaStreamWaitEvent(slot.aux[k], slot.fork, 0));
 #define G4H_STAGE(stage, on, ...)   \
@@ -424,6 +423,62 @@ int LaunchElectronPipeline(G4HB200* h, G4HB200ElectronBatch* dev, G4HB200Seconda
     G4H_CUDA(cudaStreamWaitEvent(st, slot.join[k], 0));
   }
 #undef G4H_STAGE
+  if (t.tc != nullptr) {
+    G4H_CUDA(cudaMemcpyAsync(t.tc->counts, w.count, kNumElQueues * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    G4H_CUDA(cudaEventRecord(t.tc->done, st));
+  }
+  G4H_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// fork / join streams of a work slot (created on first use)
+int EnsureAuxStreams(G4HB200::WorkSlot& slot) {
+  if (slot.fork != nullptr) return 0;
+  G4H_CUDA(cudaEventCreateWithFlags(&slot.fork, cudaEventDisableTiming));
+  for (int k = 0; k < G4HB200::WorkSlot::kNumAux; ++k) {
+    G4H_CUDA(cudaStreamCreateWithFlags(&slot.aux[k], cudaStreamNonBlocking));
+    G4H_CUDA(cudaEventCreateWithFlags(&slot.join[k], cudaEventDisableTiming));
+  }
+  return 0;
+}
+
+// G4HepEmGammaManager::[HowFar +] SelectInteraction + Perform as a pipeline: head over every track, then the three
+// final state samplers side by side over their queues (g4h_pipeline.cuh); kMode 1: Perform, 2: fused step
+template <int kMode>
+int LaunchGammaPipeline(G4HB200* h, G4HB200GammaBatch* dev, G4HB200SecondaryQueue* sec, uint64_t seed, void* stream) {
+  int rc = CheckHandle(h);
+  if (rc != 0) return rc;
+  if (dev == nullptr || dev->n < 0) return Fail(G4HB200_EINVAL, "bad gamma batch");
+  if (sec == nullptr) return Fail(G4HB200_EINVAL, "secondary queue required");
+  if (dev->n == 0) return 0;
+  if (dev->n > 0x7fffffff) return Fail(G4HB200_EINVAL, "batch too large (track indices are 32 bit)");
+  G4HB200::WorkSlot& slot = h->gmSlot;
+  if ((rc = EnsureElectronWork(slot, dev->n)) != 0) return rc;
+  if ((rc = EnsureAuxStreams(slot)) != 0) return rc;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int64_t n = dev->n;
+  const ElectronWork& w = slot.work;
+  G4H_CUDA(cudaMemsetAsync(w.count, 0, kNumElQueues * sizeof(int32_t), st));
+  StageTimer t{h, st};
+  G4H_CUDA(t.Begin(n));
+  G4H_CUDA(t.Before(kSGammaHead));
+  GammaHeadKernel<kMode><<<OneWave(h, GammaHeadKernel<kMode>, n), kThreadsPerBlock, 0, st>>>(h->view, *dev, w, seed);
+  G4H_CUDA(t.After(kSGammaHead));
+  G4H_CUDA(cudaEventRecord(slot.fork, st));
+  for (int k = 0; k < 2; ++k) G4H_CUDA(cudaStreamWaitEvent(slot.aux[k], slot.fork, 0));
+  G4H_CUDA(t.Before(kSGammaCompton, st));
+  GammaInteractKernel<kGQCompton><<<OneWave(h, GammaInteractKernel<kGQCompton>, n), kThreadsPerBlock, 0, st>>>(h->view, *dev, w, *sec, seed);
+  G4H_CUDA(t.After(kSGammaCompton, st));
+  G4H_CUDA(t.Before(kSGammaConversion, slot.aux[0]));
+  GammaInteractKernel<kGQConversion><<<OneWave(h, GammaInteractKernel<kGQConversion>, n), kThreadsPerBlock, 0, slot.aux[0]>>>(h->view, *dev, w, *sec, seed);
+  G4H_CUDA(t.After(kSGammaConversion, slot.aux[0]));
+  G4H_CUDA(t.Before(kSGammaPhotoelectric, slot.aux[1]));
+  GammaInteractKernel<kGQPhotoelectric><<<OneWave(h, GammaInteractKernel<kGQPhotoelectric>, n), kThreadsPerBlock, 0, slot.aux[1]>>>(h->view, *dev, w, *sec, seed);
+  G4H_CUDA(t.After(kSGammaPhotoelectric, slot.aux[1]));
+  for (int k = 0; k < 2; ++k) {
+    G4H_CUDA(cudaEventRecord(slot.join[k], slot.aux[k]));
+    G4H_CUDA(cudaStreamWaitEvent(st, slot.join[k], 0));
+  }
   if (t.tc != nullptr) {
     G4H_CUDA(cudaMemcpyAsync(t.tc->counts, w.count, kNumElQueues * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
     G4H_CUDA(cudaEventRecord(t.tc->done, st));
@@ -541,7 +596,8 @@ int g4hb200_destroy(G4HB200* h) {
   if (h->elCap > 0) g4hb200_electron_batch_free(h, &h->elDev);
   if (h->gmCap > 0) g4hb200_gamma_batch_free(h, &h->gmDev);
   if (h->secCap > 0) g4hb200_secondary_queue_free(h, &h->secDev);
-  for (auto& slot : h->slots) {
+  for (G4HB200::WorkSlot* sp : {&h->slots[0], &h->slots[1], &h->slots[2], &h->slots[3], &h->gmSlot}) {
+    G4HB200::WorkSlot& slot = *sp;
     if (slot.mem != nullptr) cudaFree(slot.mem);
     if (slot.stream != nullptr) cudaStreamDestroy(slot.stream);
     if (slot.counted != nullptr) cudaEventDestroy(slot.counted);
@@ -805,10 +861,12 @@ int g4hb200_gamma_howfar(G4HB200* h, G4HB200GammaBatch* dev, uint64_t seed, void
   return LaunchGamma<0>(h, dev, nullptr, seed, stream);
 }
 int g4hb200_gamma_perform(G4HB200* h, G4HB200GammaBatch* dev, G4HB200SecondaryQueue* sec, uint64_t seed, void* stream) {
-  return LaunchGamma<1>(h, dev, sec, seed, stream);
+  if (h != nullptr && h->monolith) return LaunchGamma<1>(h, dev, sec, seed, stream);
+  return LaunchGammaPipeline<1>(h, dev, sec, seed, stream);
 }
 int g4hb200_gamma_step(G4HB200* h, G4HB200GammaBatch* dev, G4HB200SecondaryQueue* sec, uint64_t seed, void* stream) {
-  return LaunchGamma<2>(h, dev, sec, seed, stream);
+  if (h != nullptr && h->monolith) return LaunchGamma<2>(h, dev, sec, seed, stream);
+  return LaunchGammaPipeline<2>(h, dev, sec, seed, stream);
 }
 
 // Host buffers in, host buffers out.  The batch is cut into chunks that travel on kNumSlots streams: while chunk c
@@ -939,7 +997,7 @@ int g4hb200_gamma_step_host(G4HB200* h, G4HB200GammaBatch* host, G4HB200Secondar
   cudaStream_t st = h->stream;
   if ((rc = CopyGamma(host, &h->gmDev, cudaMemcpyHostToDevice, st, 0, 3, true, false)) != 0) return rc;
   if ((rc = g4hb200_secondary_queue_reset(h, &h->secDev, st)) != 0) return rc;
-  if ((rc = LaunchGamma<2>(h, &h->gmDev, &h->secDev, seed, st)) != 0) return rc;
+  if ((rc = LaunchGammaPipeline<2>(h, &h->gmDev, &h->secDev, seed, st)) != 0) return rc;
   if ((rc = CopyGamma(&h->gmDev, host, cudaMemcpyDeviceToHost, st, 0, 5, true, true)) != 0) return rc;
   if ((rc = g4hb200_secondary_queue_download(h, &h->secDev, hostSec, st)) != 0) return rc;
   G4H_CUDA(cudaStreamSynchronize(st));

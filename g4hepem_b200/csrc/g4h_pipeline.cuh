@@ -268,5 +268,44 @@ ElSamplerKernel(const __grid_constant__ TablesView tv, const __grid_constant__ G
   }
 }
 
+// ---- gamma step: head over every track, one sampler kernel per process over its queue --------------------------------
+enum GmQueue { kGQConversion = 0, kGQCompton, kGQPhotoelectric, kNumGmQueues };
+
+template <int kMode>
+__global__ void __launch_bounds__(kThreadsPerBlock, G4H_MINB_QUEUE)
+GammaHeadKernel(const __grid_constant__ TablesView tv, const __grid_constant__ G4HB200GammaBatch b,
+                const __grid_constant__ ElectronWork w, uint64_t seed) {
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  const int64_t nRound = RoundUpToCta(b.n);
+  __shared__ CtaCounters<3> cc;
+  cc.Init();
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < nRound; i += stride) {
+    const int route = i < b.n ? StageGammaHead<kMode>(tv, b, i, seed) : -1;
+    RouteToQueues<3>(cc, route, static_cast<int32_t>(i), w.queue, w.count);
+  }
+}
+
+template <int kProc>
+__global__ void __launch_bounds__(kThreadsPerBlock, G4H_MINB_QUEUE)
+GammaInteractKernel(const __grid_constant__ TablesView tv, const __grid_constant__ G4HB200GammaBatch b,
+                    const __grid_constant__ ElectronWork w, const __grid_constant__ G4HB200SecondaryQueue sq, uint64_t seed) {
+  const int cnt = w.count[kProc];
+  const int nRound = static_cast<int>(RoundUpToCta(cnt));
+  const int stride = gridDim.x * blockDim.x;
+  __shared__ CtaCounters<1> cc;
+  cc.Init();
+  for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < nRound; q += stride) {
+    Secondaries sec;
+    sec.n = 0;
+    int32_t i = 0;
+    int id = 0;
+    if (q < cnt) {
+      i = w.queue[kProc][q];
+      StageGammaInteract<kProc>(tv, b, i, seed, sec, id);
+    }
+    AppendSecondaries(cc, sq, sec, id, i);
+  }
+}
+
 }  // namespace g4h
 #endif

@@ -259,5 +259,72 @@ G4H_FN void StageHowFarMSCRange(const TablesView& tv, const G4HB200ElectronBatch
   FinishHowFarMSC(b, i, s, gp.b, b.winner[i]);
 }
 
+// ---- gamma step in two stages ----------------------------------------------------------------------------------
+//   StageGammaHead       HowFar (G4HepEmGammaManager.icc:27-48; kMode 2) + SelectInteraction (.icc:173-219) +
+//                        UpdateNumIALeft and the head of Perform (.icc:54-76): returns the process that interacts
+//                        (0 conversion, 1 Compton, 2 photoelectric) or -1
+//   StageGammaInteract   the final state sampler of that process + the tracking cut (.icc:77-94), over a queue
+template <int kMode>
+G4H_FN int StageGammaHead(const TablesView& tv, const G4HB200GammaBatch& b, int64_t i, uint64_t seed) {
+  GammaState s;
+  Rng rng;
+  LoadGamma(b, i, seed, s, rng);
+  const int flags = b.meta[4 * i + 1];
+  if (kMode == 1) LoadGammaHandOver(b, i, s);
+  if (kMode == 2) GammaHowFar(tv, s, rng);
+  int route = -1;
+  if (!s.onBoundary) {
+    const double urnd = rng.Flat();
+    s.nIA0 = -1.0;
+    const double lekin = (s.ekin > tv.gmEMax1) ? GetLogEKin(s) : 0.0;
+    s.winner = GammaSampleInteraction(tv, G4H_LD(tv.mcImat + s.imc), s.ekin, lekin, s.mfp0, urnd, s.peMXsec);
+  }
+  s.nIA0 -= s.gStep / s.mfp0;
+  s.edep = 0.0;
+  if (!s.onBoundary) {
+    if (s.winner == 0) s.nIA0 = -1.0;
+    if (s.winner >= 0 && s.winner <= 2) {
+      route = s.winner;
+    } else if (s.ekin > 0.0 && s.ekin <= tv.gammaTrackingCut) {
+      // no interaction (gamma-nuclear slot): only the tracking cut of .icc:88-93 applies
+      s.edep += s.ekin;
+      SetEKin(s, 0.0);
+    }
+  }
+  StoreGamma(b, i, s, rng, flags);
+  return route;
+}
+
+template <int kProc>
+G4H_FN void StageGammaInteract(const TablesView& tv, const G4HB200GammaBatch& b, int64_t i, uint64_t seed, Secondaries& sec,
+                               int& id) {
+  const Meta m   = LoadMeta(b.meta, i);
+  const Pair e   = LoadPair(b.ekin_logekin, i);
+  const Pair dxy = LoadPair(b.dirx_diry, i);
+  const Pair dzn = LoadPair(b.dirz_nia0, i);
+  const Pair ep  = LoadPair(b.edep_pemxsec, i);
+  GammaState s;
+  s.ekin = e.a; s.logEkin = e.b;
+  s.dir[0] = dxy.a; s.dir[1] = dxy.b; s.dir[2] = dzn.a;
+  s.imc = m.imc; s.id = m.id;
+  s.edep = ep.a; s.peMXsec = ep.b;
+  id = m.id;
+  Rng rng;
+  rng.Init(seed, static_cast<uint32_t>(m.id), static_cast<uint32_t>(m.draw), false, 0.0);
+  if (kProc == 0) PerformConversion(tv, s, rng, sec);
+  if (kProc == 1) PerformCompton(s, rng, sec);
+  if (kProc == 2) PerformPhotoelectric(tv, s, rng, sec);
+  const double finalEkin = s.ekin;
+  if (finalEkin > 0.0 && finalEkin <= tv.gammaTrackingCut) {
+    SetEKin(s, 0.0);
+    s.edep += finalEkin;
+  }
+  StorePair(b.ekin_logekin, i, s.ekin, s.logEkin);
+  StorePair(b.dirx_diry, i, s.dir[0], s.dir[1]);
+  StorePair(b.dirz_nia0, i, s.dir[2], dzn.b);
+  StorePair(b.edep_pemxsec, i, s.edep, s.peMXsec);
+  StoreMeta(b.meta, i, Meta{m.imc, m.flags, m.id, static_cast<int>(rng.draw)});
+}
+
 }  // namespace g4h
 #endif

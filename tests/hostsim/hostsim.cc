@@ -135,6 +135,28 @@ int g4hsim_electron_howfar_staged(const G4HB200Tables* t, G4HB200ElectronBatch* 
   return 0;
 }
 
+// the staged gamma step / Perform (mode 2 / 1): head over the batch, then the three process queues
+int g4hsim_gamma_staged(const G4HB200Tables* t, G4HB200GammaBatch* b, G4HB200SecondaryQueue* q, uint64_t seed, int mode) {
+  const TablesView tv = MakeView(*t);
+  std::vector<int64_t> queue[3];
+  for (int64_t i = 0; i < b->n; ++i) {
+    const int route = mode == 1 ? StageGammaHead<1>(tv, *b, i, seed) : StageGammaHead<2>(tv, *b, i, seed);
+    if (route >= 0) queue[route].push_back(i);
+  }
+  for (int k = 0; k < 3; ++k) {
+    for (int64_t i : queue[k]) {
+      Secondaries sec;
+      sec.n = 0;
+      int id = 0;
+      if (k == 0) StageGammaInteract<0>(tv, *b, i, seed, sec, id);
+      if (k == 1) StageGammaInteract<1>(tv, *b, i, seed, sec, id);
+      if (k == 2) StageGammaInteract<2>(tv, *b, i, seed, sec, id);
+      AppendSec(q, sec, id, i);
+    }
+  }
+  return 0;
+}
+
 int g4hsim_gamma(const G4HB200Tables* t, G4HB200GammaBatch* b, G4HB200SecondaryQueue* q, uint64_t seed, int mode) {
   const TablesView tv = MakeView(*t);
   for (int64_t i = 0; i < b->n; ++i) {

@@ -91,3 +91,9 @@ class HostSim:
 
     def gamma_step(self, b, sec, seed):
         self._run(self.lib.g4hsim_gamma, b, sec, seed, 2)
+
+    def gamma_perform_staged(self, b, sec, seed):
+        self._run(self.lib.g4hsim_gamma_staged, b, sec, seed, 1)
+
+    def gamma_step_staged(self, b, sec, seed):
+        self._run(self.lib.g4hsim_gamma_staged, b, sec, seed, 2)

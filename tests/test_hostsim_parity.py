@@ -62,13 +62,14 @@ def test_electron_multi_step_with_geometry_stub(sim, reference, flat_tables, sta
             x.ekin_logekin[dead, 1] = 100.0
 
 
-def test_gamma_step(sim, reference, flat_tables):
+@pytest.mark.parametrize("staged", [False, True])
+def test_gamma_step(sim, reference, flat_tables, staged):
     n = 30000
     g = batches.make_gamma_batch(n, flat_tables.num_matcut, boundary_fraction=0.1)
     h = g.copy()
     qa, qb = batches.SecondaryHostQueue(2 * n), batches.SecondaryHostQueue(2 * n)
     reference.gamma_step(g, qa, 2026, 4)
-    sim.gamma_step(h, qb, 2026)
+    (sim.gamma_step_staged if staged else sim.gamma_step)(h, qb, 2026)
     rep = compare.compare_gamma_batches(g, h)
     assert compare.total_bad(rep) == 0, compare.format_report(rep, True)
     assert compare.total_bad(compare.compare_secondaries(qa, qb)) == 0

@@ -147,6 +147,31 @@ class SecondaryQueue(C.Structure):
     ]
 
 
+class SlabGeometry(C.Structure):
+    _fields_ = [
+        ("num_layers", C.c_int32),
+        ("num_absorbers", C.c_int32),
+        ("absorber_thickness", C.c_double * 4),
+        ("absorber_couple", C.c_int32 * 4),
+        ("half_yz", C.c_double),
+    ]
+
+
+class ShowerStats(C.Structure):
+    _fields_ = [
+        ("num_steps", C.c_int64),
+        ("electron_track_steps", C.c_int64),
+        ("gamma_track_steps", C.c_int64),
+        ("secondaries", C.c_int64),
+        ("peak_electrons", C.c_int64),
+        ("peak_gammas", C.c_int64),
+        ("leak_electron", C.c_double),
+        ("leak_gamma", C.c_double),
+        ("device_ms", C.c_double),
+        ("kernel_launches", C.c_int64),
+    ]
+
+
 F_POSITRON = 0x01
 F_ON_BOUNDARY = 0x02
 F_MSC_FIRST_STEP = 0x04
@@ -197,6 +222,8 @@ PROTOTYPES = {
     "g4hb200_set_kernel_timing": (C.c_int, [_H, C.c_int]),
     "g4hb200_kernel_times": (C.c_int, [_H, _vp, _vp, _vp]),
     "g4hb200_stage_name": (C.c_char_p, [C.c_int]),
+    "g4hb200_shower_run": (C.c_int, [_H, C.POINTER(SlabGeometry), C.c_int64, C.c_int32, C.c_double, C.c_uint64, C.c_int32,
+                                     C.c_int64, C.c_int32, _vp, C.POINTER(ShowerStats)]),
 }
 
 _lib = None

@@ -14,6 +14,7 @@
 #include "../../include/g4hepem_b200.h"
 #include "g4h_kernels.cuh"
 #include "g4h_pipeline.cuh"
+#include "g4h_shower.cuh"
 #include "g4h_view.cuh"
 
 using namespace g4h;
@@ -1043,3 +1044,5 @@ int g4hb200_kernel_times(G4HB200* h, double* ms_sum, int64_t* launches, int64_t*
 }
 
 }  // extern "C"
+
+#include "capi_shower.inl"

@@ -1,0 +1,205 @@
+// capi_shower.inl -- host side of g4hb200_shower_run: the stepping loop over device-resident track stores
+// (kernels: g4h_shower.cuh).  Included by capi.cu.
+namespace {
+
+struct ShowerStore {
+  G4HB200ElectronBatch el[2];
+  G4HB200GammaBatch gm[2];
+  TrackGeo elGeo[2], gmGeo[2];
+  G4HB200SecondaryQueue secEl, secGm;
+  void* geoMem = nullptr;
+  void* scoreMem = nullptr;
+  ShowerScore score;
+  int32_t* pinned = nullptr;  // {next e-, next gamma, overflow, secondaries e-, secondaries gamma}
+};
+
+int CarveGeo(unsigned char*& p, int64_t cap, TrackGeo& g) {
+  g.posx_posy = reinterpret_cast<double*>(p);
+  p += cap * 16;
+  g.posz_pad = reinterpret_cast<double*>(p);
+  p += cap * 16;
+  g.vol = reinterpret_cast<int32_t*>(p);
+  p += cap * 4;
+  g.nextVol = reinterpret_cast<int32_t*>(p);
+  p += cap * 4;
+  return 0;
+}
+
+void FreeShowerStore(G4HB200* h, ShowerStore& s) {
+  for (int k = 0; k < 2; ++k) {
+    g4hb200_electron_batch_free(h, &s.el[k]);
+    g4hb200_gamma_batch_free(h, &s.gm[k]);
+  }
+  g4hb200_secondary_queue_free(h, &s.secEl);
+  g4hb200_secondary_queue_free(h, &s.secGm);
+  if (s.geoMem != nullptr) cudaFree(s.geoMem);
+  if (s.scoreMem != nullptr) cudaFree(s.scoreMem);
+  if (s.pinned != nullptr) cudaFreeHost(s.pinned);
+}
+
+}  // namespace
+
+extern "C" int g4hb200_shower_run(G4HB200* h, const G4HB200SlabGeometry* geom, int64_t numPrimaries, int32_t primaryKind,
+                                  double primaryEkin, uint64_t seed, int32_t firstTrackId, int64_t capacity, int32_t maxSteps,
+                                  double* edepOut, G4HB200ShowerStats* stats) {
+  int rc = CheckHandle(h);
+  if (rc != 0) return rc;
+  if (geom == nullptr || edepOut == nullptr || stats == nullptr) return Fail(G4HB200_EINVAL, "null argument");
+  if (geom->num_layers < 1 || geom->num_absorbers < 1 || geom->num_absorbers > kMaxAbsorbers ||
+      geom->num_layers * geom->num_absorbers > CtaHist::kMaxBins)
+    return Fail(G4HB200_EINVAL, "bad slab geometry");
+  if (numPrimaries < 0 || numPrimaries > capacity || capacity > 0x3fffffff) return Fail(G4HB200_EINVAL, "bad primary count / capacity");
+  for (int k = 0; k < geom->num_absorbers; ++k) {
+    if (geom->absorber_couple[k] < 0 || geom->absorber_couple[k] >= h->view.numMatCut || !(geom->absorber_thickness[k] > 0.0))
+      return Fail(G4HB200_EINVAL, "bad absorber");
+  }
+  SlabGeom g;
+  std::memset(&g, 0, sizeof(g));
+  g.numLayers = geom->num_layers;
+  g.numAbsorbers = geom->num_absorbers;
+  g.absFront[0] = 0.0;
+  for (int k = 0; k < g.numAbsorbers; ++k) {
+    g.thickness[k] = geom->absorber_thickness[k];
+    g.couple[k] = geom->absorber_couple[k];
+    g.absFront[k + 1] = g.absFront[k] + g.thickness[k];
+  }
+  g.halfYZ = geom->half_yz;
+  g.xFront = -0.5 * (g.numLayers * g.absFront[g.numAbsorbers]);
+  const int nbins = g.numLayers * g.numAbsorbers;
+  std::memset(stats, 0, sizeof(*stats));
+  for (int k = 0; k < nbins; ++k) edepOut[k] = 0.0;
+  if (numPrimaries == 0) return 0;
+
+  ShowerStore s;
+  std::memset(&s, 0, sizeof(s));
+  auto fail = [&](int code) {
+    FreeShowerStore(h, s);
+    return code;
+  };
+  for (int k = 0; k < 2; ++k) {
+    if ((rc = g4hb200_electron_batch_alloc(h, capacity, &s.el[k])) != 0) return fail(rc);
+    if ((rc = g4hb200_gamma_batch_alloc(h, capacity, &s.gm[k])) != 0) return fail(rc);
+  }
+  if ((rc = g4hb200_secondary_queue_alloc(h, 2 * capacity, &s.secEl)) != 0) return fail(rc);
+  if ((rc = g4hb200_secondary_queue_alloc(h, 2 * capacity, &s.secGm)) != 0) return fail(rc);
+  {
+    const size_t per = static_cast<size_t>(capacity) * 40;
+    if (cudaMalloc(&s.geoMem, 4 * per) != cudaSuccess) return fail(Fail(G4HB200_ENOMEM, "cudaMalloc(shower geo)"));
+    unsigned char* p = static_cast<unsigned char*>(s.geoMem);
+    CarveGeo(p, capacity, s.elGeo[0]);
+    CarveGeo(p, capacity, s.elGeo[1]);
+    CarveGeo(p, capacity, s.gmGeo[0]);
+    CarveGeo(p, capacity, s.gmGeo[1]);
+    const size_t sbytes = static_cast<size_t>(nbins) * 8 + 2 * 8 + 4 * 4;
+    if (cudaMalloc(&s.scoreMem, sbytes) != cudaSuccess) return fail(Fail(G4HB200_ENOMEM, "cudaMalloc(shower score)"));
+    unsigned char* q = static_cast<unsigned char*>(s.scoreMem);
+    s.score.hist = reinterpret_cast<double*>(q);
+    s.score.leak = s.score.hist + nbins;
+    s.score.nextCount = reinterpret_cast<int32_t*>(s.score.leak + 2);
+    s.score.overflow = s.score.nextCount + 2;
+    s.score.capacity = capacity;
+    if (cudaMemset(s.scoreMem, 0, sbytes) != cudaSuccess) return fail(Fail(G4HB200_ECUDA, "cudaMemset(score)"));
+    if (cudaMallocHost(reinterpret_cast<void**>(&s.pinned), 8 * sizeof(int32_t)) != cudaSuccess)
+      return fail(Fail(G4HB200_ENOMEM, "cudaMallocHost"));
+  }
+  cudaStream_t st = h->stream;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  cudaEventCreate(&ev0);
+  cudaEventCreate(&ev1);
+  const int64_t launches0 = h->launches;
+  int cur = 0;
+  int64_t nEl = primaryKind == G4HB200_SEC_GAMMA ? 0 : numPrimaries;
+  int64_t nGm = primaryKind == G4HB200_SEC_GAMMA ? numPrimaries : 0;
+  cudaEventRecord(ev0, st);
+  ShowerPrimaryKernel<<<OneWave(h, ShowerPrimaryKernel, numPrimaries), kThreadsPerBlock, 0, st>>>(
+      g, numPrimaries, primaryKind, primaryEkin, firstTrackId, s.el[0], s.elGeo[0], s.gm[0], s.gmGeo[0]);
+  ++h->launches;
+  int status = 0;
+  for (int step = 0; (nEl > 0 || nGm > 0); ++step) {
+    if (maxSteps > 0 && step >= maxSteps) break;
+    const int nxt = cur ^ 1;
+    stats->num_steps += 1;
+    stats->electron_track_steps += nEl;
+    stats->gamma_track_steps += nGm;
+    if (nEl > stats->peak_electrons) stats->peak_electrons = nEl;
+    if (nGm > stats->peak_gammas) stats->peak_gammas = nGm;
+    cudaMemsetAsync(s.score.nextCount, 0, 2 * sizeof(int32_t), st);
+    s.el[cur].n = nEl;
+    s.gm[cur].n = nGm;
+    if (nEl > 0) {
+      G4HB200ElectronBatch& b = s.el[cur];
+      g4hb200_secondary_queue_reset(h, &s.secEl, st);
+      if ((status = g4hb200_electron_howfar(h, &b, seed, st)) != 0) break;
+      ShowerGeomKernel<false><<<OneWave(h, ShowerGeomKernel<false>, nEl), kThreadsPerBlock, 0, st>>>(
+          g, nEl, b.dirx_diry, b.dirz_safety, b.gstep_pstep, b.meta, s.elGeo[cur]);
+      ++h->launches;
+      if ((status = g4hb200_electron_perform(h, &b, &s.secEl, seed, st)) != 0) break;
+      ShowerElectronPostKernel<<<OneWave(h, ShowerElectronPostKernel, nEl), kThreadsPerBlock, 0, st>>>(
+          g, b, s.elGeo[cur], s.el[nxt], s.elGeo[nxt], s.score);
+      ++h->launches;
+    }
+    if (nGm > 0) {
+      G4HB200GammaBatch& b = s.gm[cur];
+      g4hb200_secondary_queue_reset(h, &s.secGm, st);
+      if ((status = g4hb200_gamma_howfar(h, &b, seed, st)) != 0) break;
+      ShowerGeomKernel<true><<<OneWave(h, ShowerGeomKernel<true>, nGm), kThreadsPerBlock, 0, st>>>(
+          g, nGm, b.dirx_diry, b.dirz_nia0, b.gstep_mfp0, b.meta, s.gmGeo[cur]);
+      ++h->launches;
+      if ((status = g4hb200_gamma_perform(h, &b, &s.secGm, seed, st)) != 0) break;
+      ShowerGammaPostKernel<<<OneWave(h, ShowerGammaPostKernel, nGm), kThreadsPerBlock, 0, st>>>(
+          g, b, s.gmGeo[cur], s.gm[nxt], s.gmGeo[nxt], s.score);
+      ++h->launches;
+    }
+    if (nEl > 0) {
+      ShowerSecondaryKernel<<<OneWave(h, ShowerSecondaryKernel, 2 * nEl), kThreadsPerBlock, 0, st>>>(
+          g, seed, s.secEl, s.el[cur].meta, s.elGeo[cur], s.el[nxt], s.elGeo[nxt], s.gm[nxt], s.gmGeo[nxt], s.score);
+      ++h->launches;
+      cudaMemcpyAsync(s.pinned + 3, s.secEl.count, sizeof(int32_t), cudaMemcpyDeviceToHost, st);
+    } else {
+      s.pinned[3] = 0;
+    }
+    if (nGm > 0) {
+      ShowerSecondaryKernel<<<OneWave(h, ShowerSecondaryKernel, 2 * nGm), kThreadsPerBlock, 0, st>>>(
+          g, seed, s.secGm, s.gm[cur].meta, s.gmGeo[cur], s.el[nxt], s.elGeo[nxt], s.gm[nxt], s.gmGeo[nxt], s.score);
+      ++h->launches;
+      cudaMemcpyAsync(s.pinned + 4, s.secGm.count, sizeof(int32_t), cudaMemcpyDeviceToHost, st);
+    } else {
+      s.pinned[4] = 0;
+    }
+    cudaMemcpyAsync(s.pinned, s.score.nextCount, 3 * sizeof(int32_t), cudaMemcpyDeviceToHost, st);
+    const cudaError_t err = cudaStreamSynchronize(st);
+    if (err != cudaSuccess) {
+      status = Fail(G4HB200_ECUDA, "shower step", err);
+      break;
+    }
+    if (s.pinned[2] != 0) {
+      status = Fail(G4HB200_ECAPACITY, "shower track store capacity exceeded");
+      break;
+    }
+    stats->secondaries += s.pinned[3] + s.pinned[4];
+    nEl = s.pinned[0];
+    nGm = s.pinned[1];
+    cur = nxt;
+  }
+  cudaEventRecord(ev1, st);
+  cudaEventSynchronize(ev1);
+  float ms = 0.f;
+  cudaEventElapsedTime(&ms, ev0, ev1);
+  stats->device_ms = ms;
+  stats->kernel_launches = h->launches - launches0;
+  if (status == 0) {
+    double leak[2];
+    cudaMemcpy(edepOut, s.score.hist, static_cast<size_t>(nbins) * 8, cudaMemcpyDeviceToHost);
+    cudaMemcpy(leak, s.score.leak, 16, cudaMemcpyDeviceToHost);
+    stats->leak_electron = leak[0];
+    stats->leak_gamma = leak[1];
+  }
+  cudaEventDestroy(ev0);
+  cudaEventDestroy(ev1);
+  FreeShowerStore(h, s);
+  if (status == 0) {
+    const cudaError_t err = cudaGetLastError();
+    if (err != cudaSuccess) return Fail(G4HB200_ECUDA, "shower", err);
+  }
+  return status;
+}

@@ -1,0 +1,481 @@
+// g4h_shower.cuh -- the stepping loop around HowFar / Perform for a TestEm3-style slab calorimeter, on the device.
+//
+// What the reference's callers do per track and step around the managers (G4HepEmTrackingManager::TrackElectron /
+// TrackGamma, G4HepEm/G4HepEm/src/G4HepEmTrackingManager.cc:428-705,985-1140; apps/examples/TestEm3: geometry
+// DetectorConstruction.cc:281-384, scoring SteppingAction.cc:83-84), restated for whole batches:
+//
+//   HowFar kernels          physics step limit                                           (existing pipeline)
+//   ShowerGeomKernel        distance to the slab / side faces along the direction; the step becomes
+//                           min(physics, geometry), the post-step boundary flag is set, the track is moved
+//   Perform kernels         along-step + discrete physics, secondaries into the queue    (existing pipeline)
+//   ShowerPostKernel        MSC displacement (limited by the safety like TrackingManager.cc:527-568), energy
+//                           deposit into the per-(layer, absorber) histogram, relocation into the next volume or
+//                           escape, safety for the next step, survivors compacted into the next-step store
+//   ShowerSecondaryKernel   secondaries -> new tracks at the parent's post-step point, appended to the next-step stores
+//
+// Geometry: num_layers x num_absorbers slabs stacked along x, centred on the origin, half width half_yz in y and
+// z; a track that leaves the calorimeter is dropped and its kinetic energy booked as leakage (the reference's world
+// is vacuum around the calorimeter; nothing comes back from it).
+// Track ids: a secondary's (id, first draw index) is a Philox hash of (parent id, parent draw counter after the
+// step, slot), so the streams do not depend on the order in which tracks are created or on how they are batched --
+// the loop gives the same shower breadth-first on the GPU as the depth-first CPU loop of tests/shower_oracle.py.
+#ifndef G4H_SHOWER_CUH
+#define G4H_SHOWER_CUH
+
+#include "g4h_kernels.cuh"
+
+namespace g4h {
+
+constexpr int kMaxAbsorbers = 4;
+
+struct SlabGeom {
+  int numLayers, numAbsorbers;
+  double thickness[kMaxAbsorbers];
+  double absFront[kMaxAbsorbers + 1];  // x offset of the absorber front faces inside a layer; [numAbsorbers] = layer thickness
+  int couple[kMaxAbsorbers];
+  double halfYZ, xFront;               // xFront = -0.5 * numLayers * layer thickness
+};
+
+// position / volume of the tracks of one store, next to its batch
+struct TrackGeo {
+  double* posx_posy;  // pairs
+  double* posz_pad;   // pairs {z, unused}
+  int32_t* vol;       // layer * numAbsorbers + absorber; -1: outside
+  int32_t* nextVol;   // volume behind the face the step ended on (only meaningful while on a boundary)
+};
+
+struct ShowerScore {
+  double* hist;        // [numLayers * numAbsorbers] deposited energy
+  double* leak;        // [2] kinetic energy that left the calorimeter {e-/e+, gamma}
+  int32_t* nextCount;  // [2] number of tracks in the next-step stores {e-/e+, gamma}
+  int32_t* overflow;   // [1] set when a store ran out of capacity (tracks were dropped: the run is invalid)
+  int64_t capacity;    // of every store
+};
+
+constexpr double kGeoInfinity = 1.0e+30;
+
+G4H_FN void SlabBounds(const SlabGeom& g, int vol, double& xlo, double& xhi) {
+  const int layer = vol / g.numAbsorbers;
+  const int iabs  = vol - layer * g.numAbsorbers;
+  const double layerFront = g.xFront + layer * g.absFront[g.numAbsorbers];
+  xlo = layerFront + g.absFront[iabs];
+  xhi = layerFront + g.absFront[iabs + 1];
+}
+
+G4H_FN double DistanceAlong(double p, double d, double lo, double hi) {
+  if (d > 0.) return Max(0.0, (hi - p) / d);
+  if (d < 0.) return Max(0.0, (lo - p) / d);
+  return kGeoInfinity;
+}
+
+// distance to the surface of the current slab along dir; nextVol = the volume behind that face (-1: outside)
+G4H_FN double DistanceToBoundary(const SlabGeom& g, int vol, const double* pos, const double* dir, int& nextVol) {
+  double xlo, xhi;
+  SlabBounds(g, vol, xlo, xhi);
+  const double dx = DistanceAlong(pos[0], dir[0], xlo, xhi);
+  const double dy = DistanceAlong(pos[1], dir[1], -g.halfYZ, g.halfYZ);
+  const double dz = DistanceAlong(pos[2], dir[2], -g.halfYZ, g.halfYZ);
+  const int numVol = g.numLayers * g.numAbsorbers;
+  int nv = dir[0] > 0. ? vol + 1 : vol - 1;
+  if (nv >= numVol) nv = -1;
+  double d = dx;
+  if (dy < d) { d = dy; nv = -1; }
+  if (dz < d) { d = dz; nv = -1; }
+  nextVol = nv;
+  return d;
+}
+
+// isotropic safety: distance to the nearest face of the current slab
+G4H_FN double SlabSafety(const SlabGeom& g, int vol, const double* pos) {
+  double xlo, xhi;
+  SlabBounds(g, vol, xlo, xhi);
+  double s = Min(pos[0] - xlo, xhi - pos[0]);
+  s = Min(s, g.halfYZ - fabs(pos[1]));
+  s = Min(s, g.halfYZ - fabs(pos[2]));
+  return Max(0.0, s);
+}
+
+#if defined(__CUDACC__)
+// ---- geometry step: between HowFar and Perform ------------------------------------------------------------------
+// kGamma: the batch is a gamma batch (groups gstep_mfp0 / dirz_nia0), else an e-/e+ batch (gstep_pstep / dirz_safety)
+template <bool kGamma>
+__global__ void __launch_bounds__(kThreadsPerBlock)
+ShowerGeomKernel(const __grid_constant__ SlabGeom g, int64_t n, const double* __restrict__ dirx_diry,
+                 const double* __restrict__ dirz_x, double* __restrict__ gstep_x, int32_t* __restrict__ meta,
+                 const __grid_constant__ TrackGeo geo) {
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const Pair dxy = LoadPair(dirx_diry, i);
+    const Pair dz  = LoadPair(dirz_x, i);
+    const Pair gs  = LoadPair(gstep_x, i);
+    const Pair pxy = LoadPair(geo.posx_posy, i);
+    const Pair pz  = LoadPair(geo.posz_pad, i);
+    const int vol  = geo.vol[i];
+    const double dir[3] = {dxy.a, dxy.b, dz.a};
+    double pos[3] = {pxy.a, pxy.b, pz.a};
+    int nextVol;
+    const double dist = DistanceToBoundary(g, vol, pos, dir, nextVol);
+    double step = gs.a;
+    const bool onBoundary = dist < step;
+    if (onBoundary) step = dist;
+    pos[0] += step * dir[0];
+    pos[1] += step * dir[1];
+    pos[2] += step * dir[2];
+    StorePair(gstep_x, i, step, gs.b);
+    StorePair(geo.posx_posy, i, pos[0], pos[1]);
+    StorePair(geo.posz_pad, i, pos[2], 0.0);
+    geo.nextVol[i] = nextVol;
+    int f = meta[4 * i + 1];
+    f = onBoundary ? (f | static_cast<int>(G4HB200_F_ON_BOUNDARY)) : (f & ~static_cast<int>(G4HB200_F_ON_BOUNDARY));
+    meta[4 * i + 1] = f;
+  }
+}
+
+// per CTA histogram in shared memory, flushed with one atomicAdd per touched bin
+struct CtaHist {
+  static constexpr int kMaxBins = 512;
+  double bin[kMaxBins];
+  __device__ void Init(int nbins) {
+    for (int k = threadIdx.x; k < nbins; k += blockDim.x) bin[k] = 0.0;
+    __syncthreads();
+  }
+  __device__ void Flush(double* global, int nbins) {
+    __syncthreads();
+    for (int k = threadIdx.x; k < nbins; k += blockDim.x) {
+      if (bin[k] != 0.0) atomicAdd(global + k, bin[k]);
+    }
+  }
+};
+
+// ---- after Perform: e-/e+ ----------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreadsPerBlock)
+ShowerElectronPostKernel(const __grid_constant__ SlabGeom g, const __grid_constant__ G4HB200ElectronBatch b,
+                         const __grid_constant__ TrackGeo geo, const __grid_constant__ G4HB200ElectronBatch nb,
+                         const __grid_constant__ TrackGeo ngeo, const __grid_constant__ ShowerScore sc) {
+  __shared__ CtaHist hist;
+  __shared__ CtaCounters<1> cc;
+  __shared__ double sLeak;
+  const int nbins = g.numLayers * g.numAbsorbers;
+  hist.Init(nbins);
+  cc.Init();
+  if (threadIdx.x == 0) sLeak = 0.0;
+  __syncthreads();
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  const int64_t nRound = RoundUpToCta(b.n);
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < nRound; i += stride) {
+    bool alive = false;
+    Meta m{0, 0, 0, 0};
+    Pair e{0, 0}, dxy{0, 0}, dzs{0, 0};
+    double pos[3] = {0, 0, 0};
+    int vol = -1;
+    if (i < b.n) {
+      m   = LoadMeta(b.meta, i);
+      e   = LoadPair(b.ekin_logekin, i);
+      dxy = LoadPair(b.dirx_diry, i);
+      dzs = LoadPair(b.dirz_safety, i);
+      const Pair ed  = LoadPair(b.edep_dispx, i);
+      const Pair dyz = LoadPair(b.dispy_dispz, i);
+      const Pair pxy = LoadPair(geo.posx_posy, i);
+      const Pair pz  = LoadPair(geo.posz_pad, i);
+      vol = geo.vol[i];
+      pos[0] = pxy.a; pos[1] = pxy.b; pos[2] = pz.a;
+      const bool onBoundary = (static_cast<uint32_t>(m.flags) & G4HB200_F_ON_BOUNDARY) != 0u;
+      // MSC displacement (G4HepEmTrackingManager.cc:527-568)
+      if (!onBoundary) {
+        const double disp[3] = {ed.b, dyz.a, dyz.b};
+        const double dLength2 = disp[0] * disp[0] + disp[1] * disp[1] + disp[2] * disp[2];
+        const double kGeomMinLength = 5.0e-8;
+        if (dLength2 > kGeomMinLength * kGeomMinLength) {
+          const double dispR = sqrt(dLength2);
+          const double postSafety = 0.99 * SlabSafety(g, vol, pos);
+          double scale = 0.0;
+          if (postSafety > 0.0 && dispR <= postSafety) {
+            scale = 1.0;
+          } else if (dispR < postSafety) {
+            scale = 1.0;
+          } else if (postSafety > kGeomMinLength) {
+            scale = postSafety / dispR;
+          }
+          if (scale > 0.0) {
+            pos[0] += disp[0] * scale;
+            pos[1] += disp[1] * scale;
+            pos[2] += disp[2] * scale;
+          }
+        }
+      }
+      // scoring: the deposit of this step belongs to the volume the step was made in
+      if (ed.a != 0.0) atomicAdd(&hist.bin[vol], ed.a);
+      // relocation
+      int newVol = vol;
+      int imc = m.imc;
+      if (onBoundary) {
+        newVol = geo.nextVol[i];
+        if (newVol >= 0) imc = g.couple[newVol % g.numAbsorbers];
+      }
+      alive = e.a > 0.0 && newVol >= 0;
+      if (e.a > 0.0 && newVol < 0) atomicAdd(&sLeak, e.a);
+      // keep the post-step point for the secondaries of this track
+      StorePair(geo.posx_posy, i, pos[0], pos[1]);
+      StorePair(geo.posz_pad, i, pos[2], 0.0);
+      if (alive) {
+        dzs.b = onBoundary ? 0.0 : SlabSafety(g, newVol, pos);
+        m.imc = imc;
+        vol   = newVol;
+      }
+    }
+    // survivors -> next-step store
+    const unsigned mk = __ballot_sync(0xffffffffu, alive);
+    int wb = 0;
+    const int lane = threadIdx.x & 31;
+    if (lane == 0 && mk != 0u) wb = atomicAdd(&cc.count[0], __popc(mk));
+    wb = __shfl_sync(0xffffffffu, wb, 0);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      const int t = cc.count[0];
+      cc.base[0]  = t > 0 ? atomicAdd(sc.nextCount + 0, t) : 0;
+      cc.count[0] = 0;
+    }
+    __syncthreads();
+    if (alive) {
+      const int64_t o = static_cast<int64_t>(cc.base[0]) + wb + __popc(mk & ((1u << lane) - 1u));
+      if (o >= sc.capacity) {
+        *sc.overflow = 1;
+        continue;
+      }
+      StorePair(nb.ekin_logekin, o, e.a, e.b);
+      StorePair(nb.dirx_diry, o, dxy.a, dxy.b);
+      StorePair(nb.dirz_safety, o, dzs.a, dzs.b);
+      const Pair n01 = LoadPair(b.nia01, i), n23 = LoadPair(b.nia23, i);
+      const Pair ir = LoadPair(b.msc_irange_dynrf, i), tg = LoadPair(b.msc_tlimmin_gauss, i);
+      StorePair(nb.nia01, o, n01.a, n01.b);
+      StorePair(nb.nia23, o, n23.a, n23.b);
+      StorePair(nb.msc_irange_dynrf, o, ir.a, ir.b);
+      StorePair(nb.msc_tlimmin_gauss, o, tg.a, tg.b);
+      StorePair(nb.edep_dispx, o, 0.0, 0.0);
+      StoreMeta(nb.meta, o, m);
+      nb.winner[o] = -1;
+      StorePair(ngeo.posx_posy, o, pos[0], pos[1]);
+      StorePair(ngeo.posz_pad, o, pos[2], 0.0);
+      ngeo.vol[o] = vol;
+    }
+  }
+  hist.Flush(sc.hist, nbins);
+  if (threadIdx.x == 0 && sLeak != 0.0) atomicAdd(sc.leak + 0, sLeak);
+}
+
+// ---- after Perform: gamma --------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreadsPerBlock)
+ShowerGammaPostKernel(const __grid_constant__ SlabGeom g, const __grid_constant__ G4HB200GammaBatch b,
+                      const __grid_constant__ TrackGeo geo, const __grid_constant__ G4HB200GammaBatch nb,
+                      const __grid_constant__ TrackGeo ngeo, const __grid_constant__ ShowerScore sc) {
+  __shared__ CtaHist hist;
+  __shared__ CtaCounters<1> cc;
+  __shared__ double sLeak;
+  const int nbins = g.numLayers * g.numAbsorbers;
+  hist.Init(nbins);
+  cc.Init();
+  if (threadIdx.x == 0) sLeak = 0.0;
+  __syncthreads();
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  const int64_t nRound = RoundUpToCta(b.n);
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < nRound; i += stride) {
+    bool alive = false;
+    Meta m{0, 0, 0, 0};
+    Pair e{0, 0}, dxy{0, 0}, dzn{0, 0}, pxy{0, 0}, pz{0, 0};
+    int vol = -1;
+    if (i < b.n) {
+      m   = LoadMeta(b.meta, i);
+      e   = LoadPair(b.ekin_logekin, i);
+      dxy = LoadPair(b.dirx_diry, i);
+      dzn = LoadPair(b.dirz_nia0, i);
+      const Pair ep = LoadPair(b.edep_pemxsec, i);
+      pxy = LoadPair(geo.posx_posy, i);
+      pz  = LoadPair(geo.posz_pad, i);
+      vol = geo.vol[i];
+      const bool onBoundary = (static_cast<uint32_t>(m.flags) & G4HB200_F_ON_BOUNDARY) != 0u;
+      if (ep.a != 0.0) atomicAdd(&hist.bin[vol], ep.a);
+      int newVol = vol;
+      if (onBoundary) {
+        newVol = geo.nextVol[i];
+        if (newVol >= 0) m.imc = g.couple[newVol % g.numAbsorbers];
+      }
+      alive = e.a > 0.0 && newVol >= 0;
+      if (e.a > 0.0 && newVol < 0) atomicAdd(&sLeak, e.a);
+      vol = newVol;
+    }
+    const unsigned mk = __ballot_sync(0xffffffffu, alive);
+    int wb = 0;
+    const int lane = threadIdx.x & 31;
+    if (lane == 0 && mk != 0u) wb = atomicAdd(&cc.count[0], __popc(mk));
+    wb = __shfl_sync(0xffffffffu, wb, 0);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      const int t = cc.count[0];
+      cc.base[0]  = t > 0 ? atomicAdd(sc.nextCount + 1, t) : 0;
+      cc.count[0] = 0;
+    }
+    __syncthreads();
+    if (alive) {
+      const int64_t o = static_cast<int64_t>(cc.base[0]) + wb + __popc(mk & ((1u << lane) - 1u));
+      if (o >= sc.capacity) {
+        *sc.overflow = 1;
+        continue;
+      }
+      StorePair(nb.ekin_logekin, o, e.a, e.b);
+      StorePair(nb.dirx_diry, o, dxy.a, dxy.b);
+      StorePair(nb.dirz_nia0, o, dzn.a, dzn.b);
+      const Pair ep = LoadPair(b.edep_pemxsec, i);
+      StorePair(nb.edep_pemxsec, o, 0.0, ep.b);
+      StoreMeta(nb.meta, o, m);
+      nb.winner[o] = b.winner[i];
+      StorePair(ngeo.posx_posy, o, pxy.a, pxy.b);
+      StorePair(ngeo.posz_pad, o, pz.a, 0.0);
+      ngeo.vol[o] = vol;
+    }
+  }
+  hist.Flush(sc.hist, nbins);
+  if (threadIdx.x == 0 && sLeak != 0.0) atomicAdd(sc.leak + 1, sLeak);
+}
+
+// ---- secondaries -> new tracks ----------------------------------------------------------------------------------------
+// (id, first draw) of the k-th secondary of a parent: words of one Philox block keyed by the global seed
+__device__ __forceinline__ void ChildStream(uint64_t seed, int parentId, int parentDraw, int slot, int& id, int& draw) {
+  const Philox4 r = PhiloxBlock(static_cast<uint32_t>(seed) ^ 0x5EC0DA2Au, static_cast<uint32_t>(seed >> 32),
+                                static_cast<uint32_t>(parentId), static_cast<uint32_t>(parentDraw));
+  const uint32_t a = slot == 0 ? r.x : r.z;
+  const uint32_t b = slot == 0 ? r.y : r.w;
+  id   = static_cast<int>(a);
+  draw = static_cast<int>(b & 0x3FFFFFFEu);
+}
+
+// the parents sit in a batch of one kind: only their meta (id, draw counter), position and volume are needed
+__global__ void __launch_bounds__(kThreadsPerBlock)
+ShowerSecondaryKernel(const __grid_constant__ SlabGeom g, uint64_t seed, const __grid_constant__ G4HB200SecondaryQueue q,
+                      const int32_t* __restrict__ parentMeta, const __grid_constant__ TrackGeo pgeo,
+                      const __grid_constant__ G4HB200ElectronBatch ne, const __grid_constant__ TrackGeo negeo,
+                      const __grid_constant__ G4HB200GammaBatch ng, const __grid_constant__ TrackGeo nggeo,
+                      const __grid_constant__ ShowerScore sc) {
+  __shared__ CtaCounters<2> cc;
+  cc.Init();
+  const int cnt = q.count[0];
+  const int nRound = static_cast<int>(RoundUpToCta(cnt));
+  const int stride = gridDim.x * blockDim.x;
+  for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < nRound; j += stride) {
+    int route = -1;  // 0: e-/e+ store, 1: gamma store
+    Pair dxy{0, 0}, dze{0, 0}, pxy{0, 0}, pz{0, 0};
+    int kind = 0, id = 0, draw = 0, vol = -1;
+    if (j < cnt) {
+      dxy = LoadPair(q.dirx_diry, j);
+      dze = LoadPair(q.dirz_ekin, j);
+      const int2 pk = reinterpret_cast<const int2*>(q.parent_kind)[j];
+      const int2 ps = reinterpret_cast<const int2*>(q.parent_slot)[j];
+      kind = pk.y;
+      const int p = ps.x;
+      const int parentDraw = parentMeta[4 * p + 3];
+      ChildStream(seed, pk.x, parentDraw, ps.y, id, draw);
+      pxy = LoadPair(pgeo.posx_posy, p);
+      pz  = LoadPair(pgeo.posz_pad, p);
+      vol = pgeo.vol[p];
+      route = kind == G4HB200_SEC_GAMMA ? 1 : 0;
+    }
+    // reserve slots in the two next-step stores
+    const unsigned active = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    int offset = 0;
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+      const unsigned mk = __ballot_sync(active, route == k);
+      if (mk != 0u) {
+        int wb = 0;
+        if (lane == 0) wb = atomicAdd(&cc.count[k], __popc(mk));
+        wb = __shfl_sync(active, wb, 0);
+        if (route == k) offset = wb + __popc(mk & ((1u << lane) - 1u));
+      }
+    }
+    __syncthreads();
+    if (threadIdx.x < 2) {
+      const int t = cc.count[threadIdx.x];
+      cc.base[threadIdx.x]  = t > 0 ? atomicAdd(sc.nextCount + threadIdx.x, t) : 0;
+      cc.count[threadIdx.x] = 0;
+    }
+    __syncthreads();
+    if (route < 0) continue;
+    const int64_t o = static_cast<int64_t>(cc.base[route]) + offset;
+    if (o >= sc.capacity) {
+      *sc.overflow = 1;
+      continue;
+    }
+    const double pos[3] = {pxy.a, pxy.b, pz.a};
+    const int imc = g.couple[vol % g.numAbsorbers];
+    if (route == 0) {
+      // G4HepEmElectronTrack::ReSet() state (G4HepEmTrack.hh:175-206, G4HepEmMSCTrackData.hh:54-78)
+      StorePair(ne.ekin_logekin, o, dze.b, 100.0);
+      StorePair(ne.dirx_diry, o, dxy.a, dxy.b);
+      StorePair(ne.dirz_safety, o, dze.a, SlabSafety(g, vol, pos));
+      StorePair(ne.nia01, o, -1.0, -1.0);
+      StorePair(ne.nia23, o, -1.0, -1.0);
+      StorePair(ne.msc_irange_dynrf, o, 1.0e+21, 0.04);
+      StorePair(ne.msc_tlimmin_gauss, o, 1.0e-7, 0.0);
+      StorePair(ne.edep_dispx, o, 0.0, 0.0);
+      const int flags = static_cast<int>(G4HB200_F_MSC_FIRST_STEP | (kind == G4HB200_SEC_POSITRON ? G4HB200_F_POSITRON : 0u));
+      StoreMeta(ne.meta, o, Meta{imc, flags, id, draw});
+      ne.winner[o] = -1;
+      StorePair(negeo.posx_posy, o, pos[0], pos[1]);
+      StorePair(negeo.posz_pad, o, pos[2], 0.0);
+      negeo.vol[o] = vol;
+    } else {
+      StorePair(ng.ekin_logekin, o, dze.b, 100.0);
+      StorePair(ng.dirx_diry, o, dxy.a, dxy.b);
+      StorePair(ng.dirz_nia0, o, dze.a, -1.0);
+      StorePair(ng.edep_pemxsec, o, 0.0, 0.0);
+      StoreMeta(ng.meta, o, Meta{imc, 0, id, draw});
+      ng.winner[o] = -1;
+      StorePair(nggeo.posx_posy, o, pos[0], pos[1]);
+      StorePair(nggeo.posz_pad, o, pos[2], 0.0);
+      nggeo.vol[o] = vol;
+    }
+  }
+}
+
+// primaries: at the front face of the calorimeter, along +x, entering (on the boundary)
+__global__ void __launch_bounds__(kThreadsPerBlock)
+ShowerPrimaryKernel(const __grid_constant__ SlabGeom g, int64_t n, int kind, double ekin, int firstId,
+                    const __grid_constant__ G4HB200ElectronBatch ne, const __grid_constant__ TrackGeo negeo,
+                    const __grid_constant__ G4HB200GammaBatch ng, const __grid_constant__ TrackGeo nggeo) {
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  for (int64_t o = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; o < n; o += stride) {
+    const int id = firstId + static_cast<int>(o);
+    const int imc = g.couple[0];
+    if (kind != G4HB200_SEC_GAMMA) {
+      StorePair(ne.ekin_logekin, o, ekin, 100.0);
+      StorePair(ne.dirx_diry, o, 1.0, 0.0);
+      StorePair(ne.dirz_safety, o, 0.0, 0.0);
+      StorePair(ne.nia01, o, -1.0, -1.0);
+      StorePair(ne.nia23, o, -1.0, -1.0);
+      StorePair(ne.msc_irange_dynrf, o, 1.0e+21, 0.04);
+      StorePair(ne.msc_tlimmin_gauss, o, 1.0e-7, 0.0);
+      StorePair(ne.edep_dispx, o, 0.0, 0.0);
+      const int flags = static_cast<int>(G4HB200_F_MSC_FIRST_STEP | G4HB200_F_ON_BOUNDARY |
+                                         (kind == G4HB200_SEC_POSITRON ? G4HB200_F_POSITRON : 0u));
+      StoreMeta(ne.meta, o, Meta{imc, flags, id, 0});
+      ne.winner[o] = -1;
+      StorePair(negeo.posx_posy, o, g.xFront, 0.0);
+      StorePair(negeo.posz_pad, o, 0.0, 0.0);
+      negeo.vol[o] = 0;
+    } else {
+      StorePair(ng.ekin_logekin, o, ekin, 100.0);
+      StorePair(ng.dirx_diry, o, 1.0, 0.0);
+      StorePair(ng.dirz_nia0, o, 0.0, -1.0);
+      StorePair(ng.edep_pemxsec, o, 0.0, 0.0);
+      StoreMeta(ng.meta, o, Meta{imc, static_cast<int>(G4HB200_F_ON_BOUNDARY), id, 0});
+      ng.winner[o] = -1;
+      StorePair(nggeo.posx_posy, o, g.xFront, 0.0);
+      StorePair(nggeo.posz_pad, o, 0.0, 0.0);
+      nggeo.vol[o] = 0;
+    }
+  }
+}
+#endif  // __CUDACC__
+
+}  // namespace g4h
+#endif

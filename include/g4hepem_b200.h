@@ -285,6 +285,43 @@ int g4hb200_set_kernel_timing(G4HB200* h, int enable);
 int g4hb200_kernel_times(G4HB200* h, double* ms_sum, int64_t* launches, int64_t* items);
 const char* g4hb200_stage_name(int k);
 
+/* ---- stepping loop over a slab calorimeter (BASELINE configs[4]) -----------------------------------------------
+ * The loop the reference's callers run around the managers -- G4HepEmTrackingManager::TrackElectron / TrackGamma
+ * (G4HepEm/G4HepEm/src/G4HepEmTrackingManager.cc:428-705,985-1140) inside the TestEm3 sampling calorimeter
+ * (apps/examples/TestEm3/src/DetectorConstruction.cc:281-384: num_layers x {absorbers} stacked along x, square
+ * cross section) with the per-(layer, absorber) energy-deposit score of apps/examples/TestEm3/src/SteppingAction.cc:83-84 --
+ * for num_primaries showers at once, breadth first, entirely on the device: HowFar, geometry step, Perform, MSC
+ * displacement, scoring, relocation, secondaries -> new tracks, until no track is left (or max_steps).
+ * Primaries start on the front face (x = -thickness/2) along +x.  A track leaving the calorimeter is dropped
+ * and its kinetic energy booked as leakage.  Per-track uniform streams do not depend on the batching (a secondary's
+ * stream is derived from its parent's), so edep_out is the same for any sharding of the primaries over GPUs up to
+ * floating point summation order; ranks sum their histograms with one allreduce (g4hepem_b200/sharding.py). */
+typedef struct G4HB200SlabGeometry {
+  int32_t num_layers;           /* TestEm3 fNbOfLayers (50) */
+  int32_t num_absorbers;        /* fNbOfAbsor (2), at most 4 */
+  double absorber_thickness[4]; /* mm: 2.3 (Pb), 5.7 (lAr) */
+  int32_t absorber_couple[4];   /* material-cuts couple index of each absorber */
+  double half_yz;               /* half of fCalorSizeYZ (200 mm) */
+} G4HB200SlabGeometry;
+
+typedef struct G4HB200ShowerStats {
+  int64_t num_steps;            /* iterations of the loop */
+  int64_t electron_track_steps; /* sum over iterations of the e-/e+ population */
+  int64_t gamma_track_steps;
+  int64_t secondaries;          /* tracks created */
+  int64_t peak_electrons, peak_gammas;
+  double leak_electron, leak_gamma; /* kinetic energy [MeV] that left the calorimeter */
+  double device_ms;             /* CUDA-event time of the whole loop on the handle's stream */
+  int64_t kernel_launches;
+} G4HB200ShowerStats;
+
+/* primary_kind: G4HB200_SEC_ELECTRON / _POSITRON / _GAMMA.  first_track_id: id of the first primary (ids are consecutive:
+ * give every rank its own range).  capacity: tracks per store (e-/e+ and gamma each); G4HB200_ECAPACITY if exceeded.
+ * edep_out: host array [num_layers * num_absorbers], MeV. */
+int g4hb200_shower_run(G4HB200* h, const G4HB200SlabGeometry* geom, int64_t num_primaries, int32_t primary_kind,
+                       double primary_ekin, uint64_t seed, int32_t first_track_id, int64_t capacity, int32_t max_steps,
+                       double* edep_out, G4HB200ShowerStats* stats);
+
 #ifdef __cplusplus
 }
 #endif

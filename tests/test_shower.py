@@ -1,0 +1,72 @@
+"""The slab-calorimeter stepping loop (BASELINE configs[4]): CPU restatement sanity (energy bookkeeping, independence of
+the sharding) without a GPU; the device loop against the CPU restatement, track population by track population, on the
+GPU."""
+import numpy as np
+import pytest
+
+from g4hepem_b200 import _capi, shower
+from tests import shower_oracle
+
+SEED = 2026
+
+
+def test_oracle_loop_conserves_energy(reference):
+    calo = shower.SlabCalorimeter()
+    hist, st = shower_oracle.run(reference, calo, 6, 300.0, SEED)
+    total = hist.sum() + st["leak_electron"] + st["leak_gamma"]
+    # kinetic energy in = deposits + leakage (every e+ of these showers annihilates inside: 2 m_e c^2 taken by the
+    # conversion come back as the two annihilation photons)
+    assert abs(total - 6 * 300.0) < 1e-6 * 6 * 300.0
+    assert st["num_steps"] > 20 and st["secondaries"] > 100
+    # lead (absorber 0) takes more than liquid argon per layer around the shower maximum
+    assert hist[:10, 0].sum() > hist[:10, 1].sum()
+
+
+def test_oracle_loop_does_not_depend_on_the_sharding(reference):
+    """Streams are keyed by track ids derived from the parent: two halves of the primaries give the whole."""
+    calo = shower.SlabCalorimeter(num_layers=20)
+    whole, st = shower_oracle.run(reference, calo, 8, 150.0, SEED)
+    a, sa = shower_oracle.run(reference, calo, 4, 150.0, SEED, first_track_id=0)
+    b, sb = shower_oracle.run(reference, calo, 4, 150.0, SEED, first_track_id=4)
+    np.testing.assert_allclose(a + b, whole, rtol=1e-12, atol=1e-12)
+    for k in ("electron_track_steps", "gamma_track_steps", "secondaries"):
+        assert sa[k] + sb[k] == st[k]
+
+
+def test_child_streams_are_distinct():
+    ids = np.arange(20000, dtype=np.int32)
+    draws = (np.arange(20000, dtype=np.int32) * 7) % 1000
+    i0, d0 = shower_oracle.child_stream(SEED, ids, draws, np.zeros(20000, dtype=np.int32))
+    i1, d1 = shower_oracle.child_stream(SEED, ids, draws, np.ones(20000, dtype=np.int32))
+    keys = np.concatenate([i0.astype(np.int64) << 32 | d0, i1.astype(np.int64) << 32 | d1])
+    assert len(np.unique(keys)) == keys.size
+    assert (d0 % 2 == 0).all() and (d0 >= 0).all() and (d0 < (1 << 30)).all()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("kind,nprim,ekin", [(_capi.SEC_ELECTRON, 12, 400.0), (_capi.SEC_GAMMA, 8, 250.0),
+                                             (_capi.SEC_POSITRON, 5, 100.0)])
+def test_device_shower_matches_cpu_loop(engine, reference, kind, nprim, ekin):
+    calo = shower.SlabCalorimeter()
+    want, wst = shower_oracle.run(reference, calo, nprim, ekin, SEED, kind=kind, first_track_id=100)
+    got = shower.run(engine, calo, nprim, ekin, SEED, kind=kind, first_track_id=100, capacity=1 << 16)
+    for k in ("num_steps", "electron_track_steps", "gamma_track_steps", "secondaries", "peak_electrons", "peak_gammas"):
+        assert got.stats[k] == wst[k], (k, got.stats[k], wst[k])
+    # same tracks, same deposits; the sums differ by the summation order only
+    np.testing.assert_allclose(got.edep, want, rtol=1e-9, atol=1e-9)
+    assert abs(got.stats["leak_electron"] - wst["leak_electron"]) <= 1e-9 * max(1.0, wst["leak_electron"])
+    assert abs(got.stats["leak_gamma"] - wst["leak_gamma"]) <= 1e-9 * max(1.0, wst["leak_gamma"])
+    total = got.edep.sum() + got.stats["leak_electron"] + got.stats["leak_gamma"]
+    assert abs(total - nprim * ekin) < 1e-6 * nprim * ekin or kind == _capi.SEC_POSITRON
+
+
+@pytest.mark.gpu
+def test_device_shower_sharding_and_capacity(engine):
+    calo = shower.SlabCalorimeter(num_layers=20)
+    whole = shower.run(engine, calo, 64, 200.0, SEED)
+    a = shower.run(engine, calo, 32, 200.0, SEED, first_track_id=0)
+    b = shower.run(engine, calo, 32, 200.0, SEED, first_track_id=32)
+    np.testing.assert_allclose(a.edep + b.edep, whole.edep, rtol=1e-9, atol=1e-9)
+    assert a.stats["secondaries"] + b.stats["secondaries"] == whole.stats["secondaries"]
+    with pytest.raises(_capi.G4HB200Error):
+        shower.run(engine, calo, 64, 2000.0, SEED, capacity=128)

@@ -224,6 +224,8 @@ PROTOTYPES = {
     "g4hb200_stage_name": (C.c_char_p, [C.c_int]),
     "g4hb200_shower_run": (C.c_int, [_H, C.POINTER(SlabGeometry), C.c_int64, C.c_int32, C.c_double, C.c_uint64, C.c_int32,
                                      C.c_int64, C.c_int32, _vp, C.POINTER(ShowerStats)]),
+    "g4hb200_mixed_run": (C.c_int, [_H, C.c_int64, C.c_int64, C.c_double, C.c_double, C.c_uint64, C.c_int64, C.c_int32, _vp,
+                                    C.POINTER(ShowerStats)]),
 }
 
 _lib = None

@@ -39,16 +39,61 @@ void FreeShowerStore(G4HB200* h, ShowerStore& s) {
 
 }  // namespace
 
+namespace {
+struct MixedSpec {
+  bool enabled = false;
+  int64_t nEl = 0, nGm = 0;
+  double emin = 0, emax = 0;
+};
+int RunStepLoop(G4HB200* h, const G4HB200SlabGeometry* geom, int64_t numPrimaries, int32_t primaryKind, double primaryEkin,
+                uint64_t seed, int32_t firstTrackId, int64_t capacity, int32_t maxSteps, double* edepOut,
+                G4HB200ShowerStats* stats, const MixedSpec& mixed);
+}  // namespace
+
 extern "C" int g4hb200_shower_run(G4HB200* h, const G4HB200SlabGeometry* geom, int64_t numPrimaries, int32_t primaryKind,
                                   double primaryEkin, uint64_t seed, int32_t firstTrackId, int64_t capacity, int32_t maxSteps,
                                   double* edepOut, G4HB200ShowerStats* stats) {
+  return RunStepLoop(h, geom, numPrimaries, primaryKind, primaryEkin, seed, firstTrackId, capacity, maxSteps, edepOut, stats,
+                     MixedSpec());
+}
+
+extern "C" int g4hb200_mixed_run(G4HB200* h, int64_t numElectrons, int64_t numGammas, double emin, double emax, uint64_t seed,
+                                 int64_t capacity, int32_t numSteps, double* edepTotal, G4HB200ShowerStats* stats) {
+  if (h == nullptr) return Fail(G4HB200_EINVAL, "null handle");
+  if (numElectrons < 0 || numGammas < 0 || !(emin > 0.0) || !(emax > emin) || numSteps < 1)
+    return Fail(G4HB200_EINVAL, "bad mixed workload");
+  // no geometry: a single scoring cell; a track's volume index is never used to look a couple up (secondaries
+  // inherit their parent's) and no step ends on a boundary
+  G4HB200SlabGeometry g;
+  std::memset(&g, 0, sizeof(g));
+  g.num_layers = 1;
+  g.num_absorbers = 1;
+  g.absorber_thickness[0] = 1.0;
+  g.absorber_couple[0] = 0;
+  g.half_yz = 1.0;
+  MixedSpec m;
+  m.enabled = true;
+  m.nEl = numElectrons;
+  m.nGm = numGammas;
+  m.emin = emin;
+  m.emax = emax;
+  return RunStepLoop(h, &g, numElectrons + numGammas, G4HB200_SEC_ELECTRON, 0.0, seed, 0, capacity, numSteps, edepTotal,
+                     stats, m);
+}
+
+namespace {
+int RunStepLoop(G4HB200* h, const G4HB200SlabGeometry* geom, int64_t numPrimaries, int32_t primaryKind, double primaryEkin,
+                uint64_t seed, int32_t firstTrackId, int64_t capacity, int32_t maxSteps, double* edepOut,
+                G4HB200ShowerStats* stats, const MixedSpec& mixed) {
   int rc = CheckHandle(h);
   if (rc != 0) return rc;
   if (geom == nullptr || edepOut == nullptr || stats == nullptr) return Fail(G4HB200_EINVAL, "null argument");
   if (geom->num_layers < 1 || geom->num_absorbers < 1 || geom->num_absorbers > kMaxAbsorbers ||
       geom->num_layers * geom->num_absorbers > CtaHist::kMaxBins)
     return Fail(G4HB200_EINVAL, "bad slab geometry");
-  if (numPrimaries < 0 || numPrimaries > capacity || capacity > 0x3fffffff) return Fail(G4HB200_EINVAL, "bad primary count / capacity");
+  if (numPrimaries < 0 || (mixed.enabled ? (mixed.nEl > capacity || mixed.nGm > capacity) : numPrimaries > capacity) ||
+      capacity > 0x3fffffff)
+    return Fail(G4HB200_EINVAL, "bad primary count / capacity");
   for (int k = 0; k < geom->num_absorbers; ++k) {
     if (geom->absorber_couple[k] < 0 || geom->absorber_couple[k] >= h->view.numMatCut || !(geom->absorber_thickness[k] > 0.0))
       return Fail(G4HB200_EINVAL, "bad absorber");
@@ -65,6 +110,7 @@ extern "C" int g4hb200_shower_run(G4HB200* h, const G4HB200SlabGeometry* geom, i
   }
   g.halfYZ = geom->half_yz;
   g.xFront = -0.5 * (g.numLayers * g.absFront[g.numAbsorbers]);
+  g.inheritCouple = mixed.enabled ? 1 : 0;
   const int nbins = g.numLayers * g.numAbsorbers;
   std::memset(stats, 0, sizeof(*stats));
   for (int k = 0; k < nbins; ++k) edepOut[k] = 0.0;
@@ -102,6 +148,10 @@ extern "C" int g4hb200_shower_run(G4HB200* h, const G4HB200SlabGeometry* geom, i
     if (cudaMallocHost(reinterpret_cast<void**>(&s.pinned), 8 * sizeof(int32_t)) != cudaSuccess)
       return fail(Fail(G4HB200_ENOMEM, "cudaMallocHost"));
   }
+  // size the pipelines' workspaces once (they grow on demand otherwise: a reallocation per iteration while the
+  // shower develops)
+  if ((rc = EnsureElectronWork(h->slots[0], capacity)) != 0) return fail(rc);
+  if ((rc = EnsureElectronWork(h->gmSlot, capacity)) != 0) return fail(rc);
   cudaStream_t st = h->stream;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   cudaEventCreate(&ev0);
@@ -110,9 +160,18 @@ extern "C" int g4hb200_shower_run(G4HB200* h, const G4HB200SlabGeometry* geom, i
   int cur = 0;
   int64_t nEl = primaryKind == G4HB200_SEC_GAMMA ? 0 : numPrimaries;
   int64_t nGm = primaryKind == G4HB200_SEC_GAMMA ? numPrimaries : 0;
-  cudaEventRecord(ev0, st);
-  ShowerPrimaryKernel<<<OneWave(h, ShowerPrimaryKernel, numPrimaries), kThreadsPerBlock, 0, st>>>(
-      g, numPrimaries, primaryKind, primaryEkin, firstTrackId, s.el[0], s.elGeo[0], s.gm[0], s.gmGeo[0]);
+  if (mixed.enabled) {
+    nEl = mixed.nEl;
+    nGm = mixed.nGm;
+    MixedPopulationKernel<<<OneWave(h, MixedPopulationKernel, numPrimaries), kThreadsPerBlock, 0, st>>>(
+        nEl, nGm, h->view.numMatCut, mixed.emin, mixed.emax, seed, s.el[0], s.elGeo[0], s.gm[0], s.gmGeo[0]);
+    cudaStreamSynchronize(st);  // the population is an input: keep it out of the timed loop
+    cudaEventRecord(ev0, st);
+  } else {
+    cudaEventRecord(ev0, st);
+    ShowerPrimaryKernel<<<OneWave(h, ShowerPrimaryKernel, numPrimaries), kThreadsPerBlock, 0, st>>>(
+        g, numPrimaries, primaryKind, primaryEkin, firstTrackId, s.el[0], s.elGeo[0], s.gm[0], s.gmGeo[0]);
+  }
   ++h->launches;
   int status = 0;
   for (int step = 0; (nEl > 0 || nGm > 0); ++step) {
@@ -129,11 +188,16 @@ extern "C" int g4hb200_shower_run(G4HB200* h, const G4HB200SlabGeometry* geom, i
     if (nEl > 0) {
       G4HB200ElectronBatch& b = s.el[cur];
       g4hb200_secondary_queue_reset(h, &s.secEl, st);
-      if ((status = g4hb200_electron_howfar(h, &b, seed, st)) != 0) break;
-      ShowerGeomKernel<false><<<OneWave(h, ShowerGeomKernel<false>, nEl), kThreadsPerBlock, 0, st>>>(
-          g, nEl, b.dirx_diry, b.dirz_safety, b.gstep_pstep, b.meta, s.elGeo[cur]);
-      ++h->launches;
-      if ((status = g4hb200_electron_perform(h, &b, &s.secEl, seed, st)) != 0) break;
+      if (mixed.enabled) {
+        // no geometry: the fused step (the proposed step is accepted)
+        if ((status = g4hb200_electron_step(h, &b, &s.secEl, seed, st)) != 0) break;
+      } else {
+        if ((status = g4hb200_electron_howfar(h, &b, seed, st)) != 0) break;
+        ShowerGeomKernel<false><<<OneWave(h, ShowerGeomKernel<false>, nEl), kThreadsPerBlock, 0, st>>>(
+            g, nEl, b.dirx_diry, b.dirz_safety, b.gstep_pstep, b.meta, s.elGeo[cur]);
+        ++h->launches;
+        if ((status = g4hb200_electron_perform(h, &b, &s.secEl, seed, st)) != 0) break;
+      }
       ShowerElectronPostKernel<<<OneWave(h, ShowerElectronPostKernel, nEl), kThreadsPerBlock, 0, st>>>(
           g, b, s.elGeo[cur], s.el[nxt], s.elGeo[nxt], s.score);
       ++h->launches;
@@ -141,11 +205,15 @@ extern "C" int g4hb200_shower_run(G4HB200* h, const G4HB200SlabGeometry* geom, i
     if (nGm > 0) {
       G4HB200GammaBatch& b = s.gm[cur];
       g4hb200_secondary_queue_reset(h, &s.secGm, st);
-      if ((status = g4hb200_gamma_howfar(h, &b, seed, st)) != 0) break;
-      ShowerGeomKernel<true><<<OneWave(h, ShowerGeomKernel<true>, nGm), kThreadsPerBlock, 0, st>>>(
-          g, nGm, b.dirx_diry, b.dirz_nia0, b.gstep_mfp0, b.meta, s.gmGeo[cur]);
-      ++h->launches;
-      if ((status = g4hb200_gamma_perform(h, &b, &s.secGm, seed, st)) != 0) break;
+      if (mixed.enabled) {
+        if ((status = g4hb200_gamma_step(h, &b, &s.secGm, seed, st)) != 0) break;
+      } else {
+        if ((status = g4hb200_gamma_howfar(h, &b, seed, st)) != 0) break;
+        ShowerGeomKernel<true><<<OneWave(h, ShowerGeomKernel<true>, nGm), kThreadsPerBlock, 0, st>>>(
+            g, nGm, b.dirx_diry, b.dirz_nia0, b.gstep_mfp0, b.meta, s.gmGeo[cur]);
+        ++h->launches;
+        if ((status = g4hb200_gamma_perform(h, &b, &s.secGm, seed, st)) != 0) break;
+      }
       ShowerGammaPostKernel<<<OneWave(h, ShowerGammaPostKernel, nGm), kThreadsPerBlock, 0, st>>>(
           g, b, s.gmGeo[cur], s.gm[nxt], s.gmGeo[nxt], s.score);
       ++h->launches;
@@ -203,3 +271,4 @@ extern "C" int g4hb200_shower_run(G4HB200* h, const G4HB200SlabGeometry* geom, i
   }
   return status;
 }
+}  // namespace

@@ -34,6 +34,7 @@ struct SlabGeom {
   double absFront[kMaxAbsorbers + 1];  // x offset of the absorber front faces inside a layer; [numAbsorbers] = layer thickness
   int couple[kMaxAbsorbers];
   double halfYZ, xFront;               // xFront = -0.5 * numLayers * layer thickness
+  int inheritCouple;                   // 1: no geometry (unbounded media): a secondary keeps its parent's couple
 };
 
 // position / volume of the tracks of one store, next to its batch
@@ -363,7 +364,7 @@ ShowerSecondaryKernel(const __grid_constant__ SlabGeom g, uint64_t seed, const _
   for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < nRound; j += stride) {
     int route = -1;  // 0: e-/e+ store, 1: gamma store
     Pair dxy{0, 0}, dze{0, 0}, pxy{0, 0}, pz{0, 0};
-    int kind = 0, id = 0, draw = 0, vol = -1;
+    int kind = 0, id = 0, draw = 0, vol = -1, parentImc = 0;
     if (j < cnt) {
       dxy = LoadPair(q.dirx_diry, j);
       dze = LoadPair(q.dirz_ekin, j);
@@ -372,6 +373,7 @@ ShowerSecondaryKernel(const __grid_constant__ SlabGeom g, uint64_t seed, const _
       kind = pk.y;
       const int p = ps.x;
       const int parentDraw = parentMeta[4 * p + 3];
+      parentImc = parentMeta[4 * p + 0];
       ChildStream(seed, pk.x, parentDraw, ps.y, id, draw);
       pxy = LoadPair(pgeo.posx_posy, p);
       pz  = LoadPair(pgeo.posz_pad, p);
@@ -406,7 +408,7 @@ ShowerSecondaryKernel(const __grid_constant__ SlabGeom g, uint64_t seed, const _
       continue;
     }
     const double pos[3] = {pxy.a, pxy.b, pz.a};
-    const int imc = g.couple[vol % g.numAbsorbers];
+    const int imc = g.inheritCouple ? parentImc : g.couple[vol % g.numAbsorbers];
     if (route == 0) {
       // G4HepEmElectronTrack::ReSet() state (G4HepEmTrack.hh:175-206, G4HepEmMSCTrackData.hh:54-78)
       StorePair(ne.ekin_logekin, o, dze.b, 100.0);
@@ -470,6 +472,59 @@ ShowerPrimaryKernel(const __grid_constant__ SlabGeom g, int64_t n, int kind, dou
       StoreMeta(ng.meta, o, Meta{imc, static_cast<int>(G4HB200_F_ON_BOUNDARY), id, 0});
       ng.winner[o] = -1;
       StorePair(nggeo.posx_posy, o, g.xFront, 0.0);
+      StorePair(nggeo.posz_pad, o, 0.0, 0.0);
+      nggeo.vol[o] = 0;
+    }
+  }
+}
+// BASELINE configs[3]: n tracks, one third each e-, e+, gamma, contiguous per particle and, inside a particle,
+// per couple (the queue order a stepping loop keeps); E log-uniform in [emin, emax], isotropic directions, first-step
+// state, not on a boundary.  Inputs of a synthetic workload: libdevice log/exp are fine here.
+__global__ void __launch_bounds__(kThreadsPerBlock)
+MixedPopulationKernel(int64_t nEl, int64_t nGm, int numCouples, double emin, double emax, uint64_t seed,
+                      const __grid_constant__ G4HB200ElectronBatch ne, const __grid_constant__ TrackGeo negeo,
+                      const __grid_constant__ G4HB200GammaBatch ng, const __grid_constant__ TrackGeo nggeo) {
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  const int64_t n = nEl + nGm;
+  const double lmin = log(emin), lrange = log(emax / emin);
+  for (int64_t t = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; t < n; t += stride) {
+    const bool isGamma = t >= nEl;
+    const int64_t o = isGamma ? t - nEl : t;
+    const int64_t half = nEl / 2;
+    const bool isPositron = !isGamma && o >= half;
+    const int64_t inKind = isGamma ? o : (isPositron ? o - half : o);
+    const int64_t kindSize = isGamma ? nGm : (isPositron ? nEl - half : half);
+    const int imc = static_cast<int>((inKind * numCouples) / (kindSize > 0 ? kindSize : 1));
+    const int id = static_cast<int>(t);
+    const Uniform2 u01 = UniformPair(static_cast<uint32_t>(seed) ^ 0x1A2B3C4Du, static_cast<uint32_t>(seed >> 32), static_cast<uint32_t>(id), 0u);
+    const Uniform2 u23 = UniformPair(static_cast<uint32_t>(seed) ^ 0x1A2B3C4Du, static_cast<uint32_t>(seed >> 32), static_cast<uint32_t>(id), 1u);
+    const double ekin = exp(lmin + u01.a * lrange);
+    const double cost = 2.0 * u01.b - 1.0;
+    const double sint = sqrt((1.0 - cost) * (1.0 + cost));
+    double sphi, cphi;
+    sincos(k2Pi * u23.a, &sphi, &cphi);
+    if (!isGamma) {
+      StorePair(ne.ekin_logekin, o, ekin, 100.0);
+      StorePair(ne.dirx_diry, o, sint * cphi, sint * sphi);
+      StorePair(ne.dirz_safety, o, cost, u23.b);
+      StorePair(ne.nia01, o, -1.0, -1.0);
+      StorePair(ne.nia23, o, -1.0, -1.0);
+      StorePair(ne.msc_irange_dynrf, o, 1.0e+21, 0.04);
+      StorePair(ne.msc_tlimmin_gauss, o, 1.0e-7, 0.0);
+      StorePair(ne.edep_dispx, o, 0.0, 0.0);
+      StoreMeta(ne.meta, o, Meta{imc, static_cast<int>(G4HB200_F_MSC_FIRST_STEP | (isPositron ? G4HB200_F_POSITRON : 0u)), id, 0});
+      ne.winner[o] = -1;
+      StorePair(negeo.posx_posy, o, 0.0, 0.0);
+      StorePair(negeo.posz_pad, o, 0.0, 0.0);
+      negeo.vol[o] = 0;
+    } else {
+      StorePair(ng.ekin_logekin, o, ekin, 100.0);
+      StorePair(ng.dirx_diry, o, sint * cphi, sint * sphi);
+      StorePair(ng.dirz_nia0, o, cost, -1.0);
+      StorePair(ng.edep_pemxsec, o, 0.0, 0.0);
+      StoreMeta(ng.meta, o, Meta{imc, 0, id, 0});
+      ng.winner[o] = -1;
+      StorePair(nggeo.posx_posy, o, 0.0, 0.0);
       StorePair(nggeo.posz_pad, o, 0.0, 0.0);
       nggeo.vol[o] = 0;
     }

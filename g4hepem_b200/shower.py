@@ -65,3 +65,15 @@ def run_sharded(engine, calo, total_primaries, primary_ekin, seed, rank, world, 
     total = dict(res.stats)
     total.update({k: float(v) for k, v in zip(keys, cnt)})
     return ShowerResult(hist.reshape(res.edep.shape), total), res
+
+
+def run_mixed(engine, num_electrons, num_gammas, num_steps, seed, emin=1.0e-3, emax=1.0e5, capacity=None):
+    """BASELINE configs[3]: mixed e-/e+/gamma population in queue order, `num_steps` consecutive fused steps with the
+    secondaries fed back (g4hb200_mixed_run).  Returns (deposited energy [MeV], stats)."""
+    if capacity is None:
+        capacity = 7 * max(int(num_electrons), int(num_gammas)) + (1 << 16)
+    edep = np.zeros(1, dtype=np.float64)
+    st = _capi.ShowerStats()
+    _capi.check(engine.lib.g4hb200_mixed_run(engine.handle, int(num_electrons), int(num_gammas), float(emin), float(emax),
+                                             int(seed), int(capacity), int(num_steps), edep.ctypes.data, C.byref(st)), "mixed_run")
+    return float(edep[0]), {name: getattr(st, name) for name, _ in _capi.ShowerStats._fields_}

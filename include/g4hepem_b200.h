@@ -322,6 +322,15 @@ int g4hb200_shower_run(G4HB200* h, const G4HB200SlabGeometry* geom, int64_t num_
                        double primary_ekin, uint64_t seed, int32_t first_track_id, int64_t capacity, int32_t max_steps,
                        double* edep_out, G4HB200ShowerStats* stats);
 
+/* ---- mixed stepping batches without geometry (BASELINE configs[3]) -------------------------------------------------
+ * num_electrons e-/e+ (half each) and num_gammas gammas, generated on the device in queue order (particle, then
+ * couple): E log-uniform in [emin, emax] MeV, couples uniform over the table set, isotropic.  num_steps consecutive
+ * fused steps (g4hb200_electron_step / g4hb200_gamma_step); after every step the survivors are compacted and the
+ * secondaries become tracks of the next step (a secondary keeps its parent's couple).  edep_total: one double, the
+ * energy deposited over all steps [MeV].  stats->device_ms times the loop without the generation of the population. */
+int g4hb200_mixed_run(G4HB200* h, int64_t num_electrons, int64_t num_gammas, double emin, double emax, uint64_t seed,
+                      int64_t capacity, int32_t num_steps, double* edep_total, G4HB200ShowerStats* stats);
+
 #ifdef __cplusplus
 }
 #endif

@@ -70,3 +70,16 @@ def test_device_shower_sharding_and_capacity(engine):
     assert a.stats["secondaries"] + b.stats["secondaries"] == whole.stats["secondaries"]
     with pytest.raises(_capi.G4HB200Error):
         shower.run(engine, calo, 64, 2000.0, SEED, capacity=128)
+
+
+@pytest.mark.gpu
+def test_mixed_population_steps(engine):
+    """configs[3] driver: reproducible, populations evolve, every step's e-/e+ and gamma pipelines ran."""
+    e1, s1 = shower.run_mixed(engine, 40000, 20000, 3, SEED)
+    e2, s2 = shower.run_mixed(engine, 40000, 20000, 3, SEED)
+    assert s1["num_steps"] == 3
+    for k in ("electron_track_steps", "gamma_track_steps", "secondaries", "peak_electrons", "peak_gammas"):
+        assert s1[k] == s2[k]
+    assert abs(e1 - e2) <= 1e-9 * abs(e1)
+    assert s1["electron_track_steps"] > 40000 and s1["gamma_track_steps"] > 20000
+    assert s1["secondaries"] > 10000 and e1 > 0.0

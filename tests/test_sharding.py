@@ -65,3 +65,45 @@ def test_world_size_2_gloo_matches_single_process(tmp_path, reference, flat_tabl
     want = sharding.layer_histogram(full.edep_dispx[:, 0], full.meta[:, 2] % 50, 50)
     assert np.allclose(got["hist"], want, rtol=1e-12, atol=0)
     assert got["counters"].tolist() == [n, int(sec.count[0])]
+
+
+SHOWER_WORKER = r'''
+import os, sys
+import numpy as np
+sys.path.insert(0, os.environ["G4H_ROOT"])
+import torch.distributed as dist
+from g4hepem_b200 import sharding, shower
+from oracle import checker
+from tests import shower_oracle
+dist.init_process_group("gloo")
+rank, world = dist.get_rank(), dist.get_world_size()
+ora = checker.best_available(os.path.join(os.environ["G4H_ROOT"], "tests", "golden", "hepem_state.json"))
+calo = shower.SlabCalorimeter(num_layers=20)
+lo, hi = sharding.shard_bounds(6, rank, world)
+# the CPU loop stands in for the device loop: the host logic (slice of the primaries, ids, the one collective) is tested
+hist, st = shower_oracle.run(ora, calo, hi - lo, 120.0, 2026, first_track_id=lo, threads=1)
+tot, cnt = sharding.allreduce_scores(hist.ravel(), [st["electron_track_steps"], st["gamma_track_steps"], st["secondaries"]], dist)
+if rank == 0:
+    np.savez(os.environ["G4H_OUT"], hist=tot, counters=cnt)
+dist.destroy_process_group()
+'''
+
+
+def test_sharded_showers_world_size_2_gloo(tmp_path, reference):
+    from g4hepem_b200 import shower
+    from tests import shower_oracle
+
+    out = str(tmp_path / "shower.npz")
+    script = tmp_path / "shower_worker.py"
+    script.write_text(SHOWER_WORKER)
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    env = dict(os.environ, G4H_ROOT=ROOT, G4H_OUT=out, OMP_NUM_THREADS="1")
+    subprocess.check_call([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                           "--master-addr", "127.0.0.1", "--master-port", str(port), str(script)], env=env, timeout=600)
+    got = np.load(out)
+    whole, st = shower_oracle.run(reference, shower.SlabCalorimeter(num_layers=20), 6, 120.0, 2026, threads=1)
+    np.testing.assert_allclose(got["hist"], whole.ravel(), rtol=1e-12, atol=1e-12)
+    assert list(got["counters"]) == [st["electron_track_steps"], st["gamma_track_steps"], st["secondaries"]]

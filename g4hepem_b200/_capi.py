@@ -181,7 +181,7 @@ F_MSC_NO_SCATTER = 0x20
 F_GAUSS_CACHED = 0x40
 
 SEC_ELECTRON, SEC_POSITRON, SEC_GAMMA = 0, 1, 2
-NUM_STAGES = 16
+NUM_STAGES = 20
 
 # every symbol include/g4hepem_b200.h declares: name -> (restype, argtypes)
 _vp = C.c_void_p

@@ -295,16 +295,17 @@ int EnsureElectronWork(G4HB200::WorkSlot& slot, int64_t n) {
 
 // pipeline stages of the e-/e+ step, in launch order (g4h_pipeline.cuh)
 enum ElStage {
-  kSHowFarXS = 0, kSHowFarMSC, kSHowFarMSCRange, kSContinuous, kSFluct, kSDiscrete, kSMoller, kSBhabha, kSSB, kSRB, kSAnnih, kSAtRest,
-  kSGammaHead, kSGammaConversion, kSGammaCompton, kSGammaPhotoelectric,
+  kSHowFarXS = 0, kSHowFarMSC, kSHowFarMSCRange, kSAlongStep, kSMscEl, kSMscPos, kSFluct, kSDiscrete, kSMoller, kSBhabha, kSSB, kSRB,
+  kSAnnih, kSAtRest, kSGammaHead, kSGammaConversion, kSGammaCompton, kSGammaPhotoelectric,
   kNumElStages
 };
 static_assert(kNumElStages <= G4HB200_NUM_STAGES, "G4HB200_NUM_STAGES too small");
 // pipeline stage -> queue that feeds it (-1: every track of the batch)
-const int kStageQueue[G4HB200_NUM_STAGES] = {-1, -1, kQConvRange, -1, kQFluct, kQDiscrete, kQMoller, kQBhabha, kQSB, kQRB, kQAnnih, kQAtRest,
-                                             -1, kGQConversion, kGQCompton, kGQPhotoelectric};
+const int kStageQueue[G4HB200_NUM_STAGES] = {-1, -1, kQConvRange, -1, kQMscEl, kQMscPos, kQFluct, kQDiscrete, kQMoller, kQBhabha, kQSB,
+                                             kQRB, kQAnnih, kQAtRest, -1, kGQConversion, kGQCompton, kGQPhotoelectric};
 const char* const kStageName[G4HB200_NUM_STAGES] = {
-    "ElHowFarXSKernel", "ElHowFarMSCKernel", "ElHowFarMSCRangeKernel", "ElContinuousKernel", "ElFluctuationKernel", "ElDiscreteKernel",
+    "ElHowFarXSKernel", "ElHowFarMSCKernel", "ElHowFarMSCRangeKernel", "ElAlongStepKernel", "ElMSCSampleKernel<e->",
+    "ElMSCSampleKernel<e+>", "ElFluctuationKernel", "ElDiscreteKernel",
     "ElSamplerKernel<Moller>", "ElSamplerKernel<Bhabha>", "ElSamplerKernel<SeltzerBerger>", "ElSamplerKernel<RelBrem>",
     "ElSamplerKernel<Annihilation>", "ElSamplerKernel<AtRest>", "GammaHeadKernel", "GammaInteractKernel<Conversion>",
     "GammaInteractKernel<Compton>", "GammaInteractKernel<Photoelectric>"};
@@ -400,13 +401,22 @@ int LaunchElectronPipeline(G4HB200* h, G4HB200ElectronBatch* dev, G4HB200Seconda
   G4H_CUDA(t.Before(stage));        \
   __VA_ARGS__;                      \
   G4H_CUDA(t.After(stage))
-  G4H_STAGE(kSContinuous, ElContinuousKernel<<<OneWave(h, ElContinuousKernel, n), kThreadsPerBlock, 0, st>>>(h->view, *dev, w, seed));
+  G4HB200::WorkSlot& slot = h->slots[slotIndex];
+  if ((rc = EnsureAuxStreams(slot)) != 0) return rc;
+  G4H_STAGE(kSAlongStep, ElAlongStepKernel<<<OneWave(h, ElAlongStepKernel, n), kThreadsPerBlock, 0, st>>>(h->view, *dev, w));
+  // the two particle types are scattered side by side (disjoint queues and tracks)
+  G4H_CUDA(cudaEventRecord(slot.fork, st));
+  G4H_CUDA(cudaStreamWaitEvent(slot.aux[0], slot.fork, 0));
+  G4H_STAGE(kSMscEl, ElMSCSampleKernel<false><<<OneWave(h, ElMSCSampleKernel<false>, n), kThreadsPerBlock, 0, st>>>(h->view, *dev, w, seed));
+  G4H_CUDA(t.Before(kSMscPos, slot.aux[0]));
+  ElMSCSampleKernel<true><<<OneWave(h, ElMSCSampleKernel<true>, n), kThreadsPerBlock, 0, slot.aux[0]>>>(h->view, *dev, w, seed);
+  G4H_CUDA(t.After(kSMscPos, slot.aux[0]));
+  G4H_CUDA(cudaEventRecord(slot.join[0], slot.aux[0]));
+  G4H_CUDA(cudaStreamWaitEvent(st, slot.join[0], 0));
   G4H_STAGE(kSFluct, ElFluctuationKernel<<<OneWave(h, ElFluctuationKernel, n), kThreadsPerBlock, 0, st>>>(h->view, *dev, w, seed));
   G4H_STAGE(kSDiscrete, ElDiscreteKernel<<<OneWave(h, ElDiscreteKernel, n), kThreadsPerBlock, 0, st>>>(h->view, *dev, w, seed));
 #undef G4H_STAGE
   // fork: the six samplers read disjoint queues and write disjoint tracks (+ atomic appends of secondaries)
-  G4HB200::WorkSlot& slot = h->slots[slotIndex];
-  if ((rc = EnsureAuxStreams(slot)) != 0) return rc;
   G4H_CUDA(cudaEventRecord(slot.fork, st));
   for (int k = 0; k < G4HB200::WorkSlot::kNumAux; ++k) G4H_CUDA(cudaStreamWaitEvent(slot.aux[k], slot.fork, 0));
 #define G4H_STAGE(stage, on, ...)   \
@@ -1007,7 +1017,7 @@ int g4hb200_gamma_step_host(G4HB200* h, G4HB200GammaBatch* host, G4HB200Secondar
 
 int64_t g4hb200_launch_count(const G4HB200* h) { return h != nullptr ? h->launches : 0; }
 
-const char* g4hb200_stage_name(int k) { return (k >= 0 && k < G4HB200_NUM_STAGES) ? kStageName[k] : ""; }
+const char* g4hb200_stage_name(int k) { return (k >= 0 && k < kNumElStages) ? kStageName[k] : ""; }
 
 int g4hb200_set_kernel_timing(G4HB200* h, int enable) {
   int rc = CheckHandle(h);

@@ -28,7 +28,9 @@ struct Philox4 {
 };
 
 // Philox4x32-10 block: counter = {blk, 0, id, 0}, key = {k0, k1}
-G4H_LEAF Philox4 PhiloxBlock(uint32_t k0, uint32_t k1, uint32_t id, uint32_t blk) {
+// PhiloxBlockInl: the body, for straight-line stage code (the integer rounds interleave with FP64 chains there);
+// PhiloxBlock: the out-of-line copy everything else calls
+G4H_FN Philox4 PhiloxBlockInl(uint32_t k0, uint32_t k1, uint32_t id, uint32_t blk) {
   uint32_t x0 = blk, x1 = 0u, x2 = id, x3 = 0u;
   uint32_t ka = k0, kb = k1;
 #pragma unroll
@@ -46,6 +48,8 @@ G4H_LEAF Philox4 PhiloxBlock(uint32_t k0, uint32_t k1, uint32_t id, uint32_t blk
   return Philox4{x0, x1, x2, x3};
 }
 
+G4H_LEAF Philox4 PhiloxBlock(uint32_t k0, uint32_t k1, uint32_t id, uint32_t blk) { return PhiloxBlockInl(k0, k1, id, blk); }
+
 struct Uniform2 {
   double a, b;
 };
@@ -62,6 +66,43 @@ G4H_LEAF Uniform2 UniformPair(uint32_t k0, uint32_t k1, uint32_t id, uint32_t bl
   const Philox4 r = PhiloxBlock(k0, k1, id, blk);
   return Uniform2{ToUniform(r.x, r.y), ToUniform(r.z, r.w)};
 }
+
+// The next uniforms of a track as a window u[0..4] = draws first .. first+4, generated in one go by every lane of
+// the warp (three Philox blocks cover the five draws whatever the parity of `first`): the lock-step stages take
+// their draws from it instead of calling Rng::Flat() from divergent sites.  Draw(5) (the sixth uniform) is in the
+// window when `first` is even and costs one more block otherwise.
+struct DrawWindow {
+  double u[5];
+  double v5;        // uniform 2*(blk0+2)+1: the sixth draw when `first` is even
+  uint32_t k0, k1, id, first;
+
+  G4H_MFN void Init(uint64_t seed, uint32_t trackId, uint32_t firstDraw) {
+    k0 = static_cast<uint32_t>(seed);
+    k1 = static_cast<uint32_t>(seed >> 32);
+    id = trackId;
+    first = firstDraw;
+    const uint32_t blk = firstDraw >> 1;
+    const Philox4 a = PhiloxBlockInl(k0, k1, id, blk);
+    const Philox4 b = PhiloxBlockInl(k0, k1, id, blk + 1u);
+    const Philox4 c = PhiloxBlockInl(k0, k1, id, blk + 2u);
+    const double v0 = ToUniform(a.x, a.y), v1 = ToUniform(a.z, a.w);
+    const double v2 = ToUniform(b.x, b.y), v3 = ToUniform(b.z, b.w);
+    const double v4 = ToUniform(c.x, c.y);
+    v5 = ToUniform(c.z, c.w);
+    const bool odd = (firstDraw & 1u) != 0u;
+    u[0] = odd ? v1 : v0;
+    u[1] = odd ? v2 : v1;
+    u[2] = odd ? v3 : v2;
+    u[3] = odd ? v4 : v3;
+    u[4] = odd ? v5 : v4;
+  }
+  // the sixth uniform of the window (draw first+5)
+  G4H_MFN double Sixth() const {
+    if ((first & 1u) == 0u) return v5;
+    const Philox4 d = PhiloxBlock(k0, k1, id, (first >> 1) + 3u);
+    return ToUniform(d.x, d.y);
+  }
+};
 
 struct Rng {
   uint32_t k0, k1;  // key: global seed

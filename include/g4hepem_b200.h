@@ -280,7 +280,7 @@ int64_t g4hb200_launch_count(const G4HB200* h);
  * pipeline stage k < G4HB200_NUM_STAGES, the summed device time in ms (ms_sum[k]), the number of launches
  * (launches[k]) and the summed number of tracks the stage processed (items[k], from the queue counters);
  * the sums restart at every call.  Stage names: g4hb200_stage_name(k). */
-#define G4HB200_NUM_STAGES 16 /* capacity; unused slots have an empty name and zero launches */
+#define G4HB200_NUM_STAGES 20 /* capacity; unused slots have an empty name and zero launches */
 int g4hb200_set_kernel_timing(G4HB200* h, int enable);
 int g4hb200_kernel_times(G4HB200* h, double* ms_sum, int64_t* launches, int64_t* items);
 const char* g4hb200_stage_name(int k);

@@ -8,6 +8,7 @@
 #include <vector>
 
 #include "../../g4hepem_b200/csrc/g4h_batch_io.cuh"
+#include "../../g4hepem_b200/csrc/g4h_perform_stages.cuh"
 #include "../../g4hepem_b200/csrc/g4h_stages.cuh"
 #include "../../g4hepem_b200/csrc/g4h_view.cuh"
 
@@ -132,6 +133,50 @@ int g4hsim_electron_howfar_staged(const G4HB200Tables* t, G4HB200ElectronBatch* 
     if (StageHowFarMSC<true>(tv, *b, i, seed)) queue.push_back(i);
   }
   for (int64_t i : queue) StageHowFarMSCRange(tv, *b, i);
+  return 0;
+}
+
+// the staged Perform (g4h_perform_stages.cuh), stage after stage over the queues like the kernels do
+int g4hsim_electron_perform_staged(const G4HB200Tables* t, G4HB200ElectronBatch* b, G4HB200SecondaryQueue* q, uint64_t seed) {
+  const TablesView tv = MakeView(*t);
+  std::vector<double> prestep(2 * static_cast<size_t>(b->n) + 2);
+  std::vector<int64_t> queue[kNumElQueues];
+  for (int64_t i = 0; i < b->n; ++i) {
+    const int r = StageAlongStep(tv, *b, prestep.data(), i);
+    if (r >= 0) queue[r].push_back(i);
+  }
+  const double cbeta1 = MscCBeta1();
+  for (int64_t i : queue[kQMscEl]) {
+    const int r = StageMSCSample<false>(tv, *b, prestep.data(), i, seed, cbeta1);
+    if (r >= 0) queue[r].push_back(i);
+  }
+  for (int64_t i : queue[kQMscPos]) {
+    const int r = StageMSCSample<true>(tv, *b, prestep.data(), i, seed, cbeta1);
+    if (r >= 0) queue[r].push_back(i);
+  }
+  for (int64_t i : queue[kQFluct]) {
+    const int r = StageFluctuation(tv, *b, prestep.data(), i, seed);
+    if (r >= 0) queue[r].push_back(i);
+  }
+  for (int64_t i : queue[kQDiscrete]) {
+    const int r = StageDiscrete(tv, *b, i, seed);
+    if (r >= 0) queue[r].push_back(i);
+  }
+  for (int k : {static_cast<int>(kQMoller), static_cast<int>(kQBhabha), static_cast<int>(kQSB), static_cast<int>(kQRB),
+                static_cast<int>(kQAnnih), static_cast<int>(kQAtRest)}) {
+    for (int64_t i : queue[k]) {
+      Secondaries sec;
+      sec.n = 0;
+      int id = 0;
+      if (k == kQMoller) StageSampler<kQMoller>(tv, *b, i, seed, sec, id);
+      if (k == kQBhabha) StageSampler<kQBhabha>(tv, *b, i, seed, sec, id);
+      if (k == kQSB) StageSampler<kQSB>(tv, *b, i, seed, sec, id);
+      if (k == kQRB) StageSampler<kQRB>(tv, *b, i, seed, sec, id);
+      if (k == kQAnnih) StageSampler<kQAnnih>(tv, *b, i, seed, sec, id);
+      if (k == kQAtRest) StageSampler<kQAtRest>(tv, *b, i, seed, sec, id);
+      AppendSec(q, sec, id, i);
+    }
+  }
   return 0;
 }
 

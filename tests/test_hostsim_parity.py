@@ -52,7 +52,7 @@ def test_electron_multi_step_with_geometry_stub(sim, reference, flat_tables, sta
             x.gstep_pstep[cut, 0] *= f[cut]
             x.meta[:, 1] = np.where(cut, x.meta[:, 1] | _capi.F_ON_BOUNDARY, x.meta[:, 1] & ~_capi.F_ON_BOUNDARY)
         reference.electron_perform(a, qa, 2026, 4)
-        sim.electron_perform(b, qb, 2026)
+        (sim.electron_perform_staged if staged else sim.electron_perform)(b, qb, 2026)
         rep = compare.compare_electron_batches(a, b)
         assert compare.total_bad(rep) == 0, compare.format_report(rep, True)
         assert compare.total_bad(compare.compare_secondaries(qa, qb)) == 0

@@ -47,7 +47,9 @@ STAGE_BYTES = {
     "ElHowFarXSKernel": (3 * 16 + 16, 7 * 16 + 16 + 4, 0),
     "ElHowFarMSCKernel": (7 * 16 + 16 + 4, 8 * 16 + 16 + 4, 0),
     "ElHowFarMSCRangeKernel": (4 + 3 * 16 + 16 + 4, 4 * 16 + 4, 0),
-    "ElContinuousKernel": (7 * 16 + 16 + 9 * 16 + 4, 10 * 16 + 16 + 4 + 16 + 16, 0),
+    "ElAlongStepKernel": (11 * 16 + 16 + 4, 7 * 16, 0),
+    "ElMSCSampleKernel<e->": (4 + 10 * 16 + 16 + 4, 4 * 16 + 16, 0),
+    "ElMSCSampleKernel<e+>": (4 + 10 * 16 + 16 + 4, 4 * 16 + 16, 0),
     "ElFluctuationKernel": (4 + 16 + 3 * 16 + 4, 3 * 16 + 16, 0),
     "ElDiscreteKernel": (4 + 16 + 16 + 4 + 16 + 16, 3 * 16, 0),
     "ElSamplerKernel<Moller>": (4 + 16 + 3 * 16, 3 * 16 + 16, 1),
@@ -370,11 +372,12 @@ def run_gpu(args):
 
 def _traffic_from_profile(kernel):
     """dram bytes read+written per launch of `kernel` from the committed `ncu --set full` summary."""
-    path = os.path.join(ROOT, "profiles", "r01_pipeline_full.json")
+    path = os.path.join(ROOT, "profiles", "r01c_pipeline_full.json")
+    ncu_name = kernel.replace("<e->", "<0>").replace("<e+>", "<1>")
     if os.path.exists(path):
         try:
             with open(path) as f:
-                return json.load(f).get(kernel, {}).get("dram_bytes_per_launch")
+                return json.load(f).get(ncu_name, {}).get("dram_bytes_per_launch")
         except (OSError, ValueError):
             return None
     return None

@@ -295,16 +295,16 @@ int EnsureElectronWork(G4HB200::WorkSlot& slot, int64_t n) {
 
 // pipeline stages of the e-/e+ step, in launch order (g4h_pipeline.cuh)
 enum ElStage {
-  kSHowFarXS = 0, kSHowFarMSC, kSHowFarMSCRange, kSAlongStep, kSMscEl, kSMscPos, kSFluct, kSDiscrete, kSMoller, kSBhabha, kSSB, kSRB,
+  kSHowFarXS = 0, kSHowFarMSC, kSAlongStep, kSMscEl, kSMscPos, kSFluct, kSDiscrete, kSMoller, kSBhabha, kSSB, kSRB,
   kSAnnih, kSAtRest, kSGammaHead, kSGammaConversion, kSGammaCompton, kSGammaPhotoelectric,
   kNumElStages
 };
 static_assert(kNumElStages <= G4HB200_NUM_STAGES, "G4HB200_NUM_STAGES too small");
 // pipeline stage -> queue that feeds it (-1: every track of the batch)
-const int kStageQueue[G4HB200_NUM_STAGES] = {-1, -1, kQConvRange, -1, kQMscEl, kQMscPos, kQFluct, kQDiscrete, kQMoller, kQBhabha, kQSB,
+const int kStageQueue[G4HB200_NUM_STAGES] = {-1, -1, -1, kQMscEl, kQMscPos, kQFluct, kQDiscrete, kQMoller, kQBhabha, kQSB,
                                              kQRB, kQAnnih, kQAtRest, -1, kGQConversion, kGQCompton, kGQPhotoelectric};
 const char* const kStageName[G4HB200_NUM_STAGES] = {
-    "ElHowFarXSKernel", "ElHowFarMSCKernel", "ElHowFarMSCRangeKernel", "ElAlongStepKernel", "ElMSCSampleKernel<e->",
+    "ElHowFarXSKernel", "ElHowFarMSCKernel", "ElAlongStepKernel", "ElMSCSampleKernel<e->",
     "ElMSCSampleKernel<e+>", "ElFluctuationKernel", "ElDiscreteKernel",
     "ElSamplerKernel<Moller>", "ElSamplerKernel<Bhabha>", "ElSamplerKernel<SeltzerBerger>", "ElSamplerKernel<RelBrem>",
     "ElSamplerKernel<Annihilation>", "ElSamplerKernel<AtRest>", "GammaHeadKernel", "GammaInteractKernel<Conversion>",
@@ -353,11 +353,8 @@ int LaunchHowFarStages(G4HB200* h, G4HB200ElectronBatch* dev, const ElectronWork
   ElHowFarXSKernel<<<OneWave(h, ElHowFarXSKernel, n), kThreadsPerBlock, 0, st>>>(h->view, *dev, seed);
   G4H_CUDA(t.After(kSHowFarXS));
   G4H_CUDA(t.Before(kSHowFarMSC));
-  ElHowFarMSCKernel<kStoreResults><<<OneWave(h, ElHowFarMSCKernel<kStoreResults>, n), kThreadsPerBlock, 0, st>>>(h->view, *dev, w, seed);
+  ElHowFarMSCKernel<kStoreResults><<<OneWave(h, ElHowFarMSCKernel<kStoreResults>, n), kThreadsPerBlock, 0, st>>>(h->view, *dev, seed);
   G4H_CUDA(t.After(kSHowFarMSC));
-  G4H_CUDA(t.Before(kSHowFarMSCRange));
-  ElHowFarMSCRangeKernel<<<OneWave(h, ElHowFarMSCRangeKernel, n), kThreadsPerBlock, 0, st>>>(h->view, *dev, w);
-  G4H_CUDA(t.After(kSHowFarMSCRange));
   return 0;
 }
 

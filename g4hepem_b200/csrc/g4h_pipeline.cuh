@@ -32,10 +32,18 @@ namespace g4h {
 #define G4H_MINB_XS 3
 #endif
 #ifndef G4H_MINB_MSCLIM
-#define G4H_MINB_MSCLIM 4
+#define G4H_MINB_MSCLIM 3
 #endif
 #ifndef G4H_MINB_ALONG
 #define G4H_MINB_ALONG 3
+#endif
+// draw windows (uniforms per track pre-generated at full warp width, g4h_rng.cuh): the fluctuation sampler takes
+// ~9 draws per track on average, the rejection samplers 3-11
+#ifndef G4H_WINDOW_FLUCT
+#define G4H_WINDOW_FLUCT 16
+#endif
+#ifndef G4H_WINDOW_SAMPLER
+#define G4H_WINDOW_SAMPLER 8
 #endif
 #ifndef G4H_MINB_MSC
 #define G4H_MINB_MSC 3
@@ -50,25 +58,10 @@ ElHowFarXSKernel(const __grid_constant__ TablesView tv, const __grid_constant__ 
 
 template <bool kStoreResults>
 __global__ void __launch_bounds__(kThreadsPerBlock, G4H_MINB_MSCLIM)
-ElHowFarMSCKernel(const __grid_constant__ TablesView tv, const __grid_constant__ G4HB200ElectronBatch b,
-                  const __grid_constant__ ElectronWork w, uint64_t seed) {
+ElHowFarMSCKernel(const __grid_constant__ TablesView tv, const __grid_constant__ G4HB200ElectronBatch b, uint64_t seed) {
   const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
-  const int64_t nRound = RoundUpToCta(b.n);
-  __shared__ CtaCounters<1> cc;
-  cc.Init();
-  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < nRound; i += stride) {
-    const bool queued = i < b.n && StageHowFarMSC<kStoreResults>(tv, b, i, seed);
-    RouteToQueues<1>(cc, queued ? 0 : -1, static_cast<int32_t>(i), w.queue + kQConvRange, w.count + kQConvRange);
-  }
-}
-
-__global__ void __launch_bounds__(kThreadsPerBlock, G4H_MINB_QUEUE)
-ElHowFarMSCRangeKernel(const __grid_constant__ TablesView tv, const __grid_constant__ G4HB200ElectronBatch b,
-                       const __grid_constant__ ElectronWork w) {
-  const int cnt = w.count[kQConvRange];
-  const int stride = gridDim.x * blockDim.x;
-  for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < cnt; q += stride) {
-    StageHowFarMSCRange(tv, b, w.queue[kQConvRange][q]);
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < b.n; i += stride) {
+    StageHowFarMSC<kStoreResults>(tv, b, i, seed);
   }
 }
 
@@ -118,13 +111,14 @@ ElFluctuationKernel(const __grid_constant__ TablesView tv, const __grid_constant
   const int nRound = static_cast<int>(RoundUpToCta(cnt));
   const int stride = gridDim.x * blockDim.x;
   __shared__ CtaCounters<2> cc;
+  __shared__ double window[G4H_WINDOW_FLUCT * kThreadsPerBlock];
   cc.Init();
   for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < nRound; q += stride) {
     int route = -1;
     int32_t i = 0;
     if (q < cnt) {
       i = w.queue[kQFluct][q];
-      route = StageFluctuation(tv, b, w.prestep, i, seed);
+      route = StageFluctuation(tv, b, w.prestep, i, seed, window + threadIdx.x, kThreadsPerBlock, G4H_WINDOW_FLUCT);
     }
     RouteToQueues<2>(cc, route < 0 ? -1 : route - kQDiscrete, i, w.queue + kQDiscrete, w.count + kQDiscrete);
   }
@@ -160,6 +154,8 @@ ElSamplerKernel(const __grid_constant__ TablesView tv, const __grid_constant__ G
   const int nRound = static_cast<int>(RoundUpToCta(cnt));
   const int stride = gridDim.x * blockDim.x;
   __shared__ CtaCounters<1> cc;
+  constexpr uint32_t kSlots = kQueue == kQAtRest ? 2 : (kQueue == kQBhabha ? 2 * G4H_WINDOW_SAMPLER : G4H_WINDOW_SAMPLER);
+  __shared__ double window[kSlots * kThreadsPerBlock];
   cc.Init();
   for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < nRound; q += stride) {
     Secondaries sec;
@@ -168,7 +164,7 @@ ElSamplerKernel(const __grid_constant__ TablesView tv, const __grid_constant__ G
     int id = 0;
     if (q < cnt) {
       i = w.queue[kQueue][q];
-      StageSampler<kQueue>(tv, b, i, seed, sec, id);
+      StageSampler<kQueue>(tv, b, i, seed, sec, id, window + threadIdx.x, kThreadsPerBlock, kSlots);
     }
     AppendSecondaries(cc, sq, sec, id, i);
   }

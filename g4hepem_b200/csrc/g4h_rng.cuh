@@ -112,6 +112,12 @@ struct Rng {
   double next;
   bool hasGauss;    // G4HepEmRandomEngine::fIsGauss
   double gauss;     // G4HepEmRandomEngine::fGauss
+  // optional window of pre-generated uniforms (queue kernels, shared memory): win[k * winStride] is draw winFirst + k.
+  // Rejection and Poisson loops consume a data dependent number of draws per track; generated one block at a time
+  // from inside those loops the Philox rounds ran at 8 of 32 lanes (42 % of the instructions of the fluctuation
+  // kernel, profiles/r01c_*), generated up front every lane of the warp works.
+  const double* win;
+  uint32_t winFirst, winCount, winStride;
 
   G4H_MFN void Init(uint64_t seed, uint32_t trackId, uint32_t firstDraw, bool isGauss, double gaussVal) {
     k0 = static_cast<uint32_t>(seed);
@@ -122,12 +128,33 @@ struct Rng {
     next = 0.0;
     hasGauss = isGauss;
     gauss = gaussVal;
+    win = nullptr;
+    winFirst = 0u;
+    winCount = 0u;
+    winStride = 0u;
+  }
+
+  // fill `slots` (even) window entries starting at the block that holds the next draw; call right after Init
+  G4H_MFN void FillWindow(double* window, uint32_t stride, uint32_t slots) {
+    const uint32_t blk0 = draw >> 1;
+#pragma unroll 1
+    for (uint32_t k = 0; k < slots; k += 2) {
+      const Uniform2 u = UniformPair(k0, k1, id, blk0 + (k >> 1));
+      window[k * stride]        = u.a;
+      window[(k + 1u) * stride] = u.b;
+    }
+    win = window;
+    winFirst = blk0 << 1;
+    winCount = slots;
+    winStride = stride;
   }
 
   // G4HepEmRandomEngine::flat(): draws are consumed strictly in order, so the second uniform of a block is
   // always the next one asked for
   G4H_MFN double Flat() {
     const uint32_t j = draw++;
+    const uint32_t k = j - winFirst;
+    if (k < winCount) return win[k * winStride];
     if (hasNext) {
       hasNext = false;
       return next;

@@ -18,6 +18,7 @@
 #define G4H_STAGES_CUH
 
 #include "g4h_batch_io.cuh"
+#include "g4h_perform_stages.cuh"
 
 namespace g4h {
 
@@ -161,49 +162,176 @@ G4H_FN void StageHowFarXS(const TablesView& tv, const G4HB200ElectronBatch& b, i
 }
 
 // ---- HowFar, part 2 -----------------------------------------------------------------------------------------
-// the end of HowFarToMSC (.icc:155-163) once zPath is known
-G4H_FN void FinishHowFarMSC(const G4HB200ElectronBatch& b, int64_t i, const ElectronState& s, double pStepLength, int winner) {
-  if (s.trueStep < pStepLength) {
-    winner      = -2;
-    pStepLength = s.trueStep;
+// HowFarToMSC (.icc:103-164) on registers, in lock step: Urban StepLimit (UMSC.icc:19-126) and all four regimes of
+// ConvertTrueToGeometricLength (.icc:602-650) through ONE sequence of Exp / inverse range / Log / spline / Log / Exp
+// that every lane of the warp walks; a lane selects the result of the regime it is in.  (The branchy version ran
+// at 12.5 of 32 lanes and sent the inverse-range regime, one track in seven, through a queue and a third kernel.)
+//   in : s.ekin, logEkin, imc, isPositron, onBoundary, mscFirstStep, safety, range, lambtr1, pStep, winner,
+//        initialRange, dynRangeFactor, tlimitMin; the Gauss cache; uA, uB = draws `draw`, `draw + 1` of the track
+//   out: s.trueStep, zPath, par1-3, mscActive / mscDisplace / mscNoScatter / mscFirstStep, initialRange,
+//        dynRangeFactor, tlimitMin, pStep, gStep, winner; returns the number of uniforms consumed
+G4H_FN int HowFarMSCCore(const TablesView& tv, ElectronState& s, bool& hasGauss, double& gauss, double uA, double uB,
+                         uint32_t k0, uint32_t k1, uint32_t draw) {
+  const double pStepLength = s.pStep;
+  s.trueStep = pStepLength;
+  s.zPath    = pStepLength;
+  s.par1 = -1.; s.par2 = 0.; s.par3 = 0.;
+  s.mscActive = false;
+  if (!MSCStepLimitApplies(pStepLength, s.ekin)) return 0;  // .icc:117-132; the MSC flags keep their values
+  s.mscActive = true;
+  const bool isElectron = !s.isPositron;
+  const ElectronTablesView& et = tv.el[isElectron ? 0 : 1];
+  const int imat = G4H_LD(tv.mcImat + s.imc);
+  const double* mp = tv.matPars + 16 * imat;
+  const double* rp = tv.regionPars + 8 * G4H_LD(tv.mcIreg + s.imc);
+  const double range = s.range, presafety = s.safety, ekin = s.ekin, lam = s.lambtr1;
+  // --- UMSC::StepLimit (UMSC.icc:19-126)
+  const double kTLimitMinfix = 1.0E-8;
+  s.mscNoScatter = false;
+  s.mscDisplace  = true;
+  const bool noLimit = s.trueStep < kTLimitMinfix || range * G4H_LD(mp + kMUMSCPar) < presafety;
+  if (noLimit) s.mscDisplace = false;
+  double tlimit = 0.0;
+  if (!noLimit) {
+    const double mscRangeFactor  = G4H_LD(rp + kRMSCRangeFactor);
+    const double mscSafetyFactor = G4H_LD(rp + kRMSCSafetyFactor);
+    const bool mscIsUseSafety    = !(G4H_LD(rp + kRIsMSCMinimal) != 0.0);
+    if (mscIsUseSafety) {
+      if (s.mscFirstStep || s.onBoundary) {
+        s.initialRange   = Max(range, lam);
+        s.dynRangeFactor = lam > 1.0 ? mscRangeFactor * (0.75 + 0.25 * lam) : mscRangeFactor;
+        const double stepMin = FastDiv(lam * 1.0E-3, 2.0E-3 + ekin * (G4H_LD(mp + kMStepMin0) + ekin * G4H_LD(mp + kMStepMin1)));
+        const double dum0 = isElectron ? 0.87 * G4H_LD(mp + kMZeff23) : 0.70 * G4H_LD(mp + kMZeffSqrt);
+        const double dum1 = ekin > 5.0E-3 ? dum0 * stepMin : dum0 * stepMin * 0.5 * (1.0 + ekin * 200.0);
+        s.tlimitMin    = Max(dum1, kTLimitMinfix);
+        s.mscFirstStep = false;
+      }
+      tlimit = range > presafety ? Max(Max(s.initialRange * s.dynRangeFactor, mscSafetyFactor * presafety), s.tlimitMin)
+                                 : Max(range, s.tlimitMin);
+    } else {
+      if (s.onBoundary) {
+        const double tmpTlimit = range > lam ? mscRangeFactor * range : mscRangeFactor * lam;
+        s.initialRange = Max(tmpTlimit, 10 * kTLimitMinfix);
+      }
+      tlimit = s.initialRange;
+    }
   }
-  const double gStep = Min(s.zPath, pStepLength);
-  StorePair(b.tstep_zpath, i, s.trueStep, s.zPath);
-  StorePair(b.par12, i, s.par1, s.par2);
-  StorePair(b.par3_pad, i, s.par3, 0.0);
-  StorePair(b.gstep_pstep, i, gStep, pStepLength);
-  b.winner[i] = winner;
+  // the Gaussian smearing of the limit (UMSC.icc:117-125) with G4HepEmRandomEngine::Gauss (RandomEngine.hh:50-67):
+  // the first pair of uniforms comes from the caller, the logarithm is taken by every lane
+  const double tlimitmin = s.tlimitMin;
+  const bool smear     = !noLimit && tlimit < s.trueStep;
+  const bool needGauss = smear && tlimit > tlimitmin;
+  const bool newGauss  = needGauss && !hasGauss;
+  int nDraw = 0;
+  double v1 = 0.5, v2 = 0.5, r = 0.5;
+  if (newGauss) {
+    v1 = 2. * uA - 1.;
+    v2 = 2. * uB - 1.;
+    r  = v1 * v1 + v2 * v2;
+    nDraw = 2;
+    while (r > 1.) {  // 21 % of the pairs are rejected
+      const uint32_t j = draw + static_cast<uint32_t>(nDraw);
+      const Uniform2 p = UniformPair(k0, k1, s.id, j >> 1);
+      const double w0  = (j & 1u) ? p.b : p.a;
+      const double w1  = (j & 1u) ? UniformPair(k0, k1, s.id, (j >> 1) + 1u).a : p.b;
+      v1 = 2. * w0 - 1.;
+      v2 = 2. * w1 - 1.;
+      r  = v1 * v1 + v2 * v2;
+      nDraw += 2;
+    }
+  }
+  const double fac = sqrt(-2. * LogInl(r) / r);
+  if (needGauss) {
+    const double stDev = 0.1 * (tlimit - tlimitmin);
+    double g;
+    if (hasGauss) {
+      hasGauss = false;
+      g = gauss * stDev + tlimit;
+    } else {
+      gauss    = v1 * fac;
+      hasGauss = true;
+      g = v2 * fac * stDev + tlimit;
+    }
+    s.trueStep = Min(Max(g, tlimitmin), s.trueStep);
+  } else if (smear) {
+    s.trueStep = Min(tlimitmin, s.trueStep);
+  }
+  // --- ConvertTrueToGeometricLength (.icc:602-650), the four regimes side by side
+  s.trueStep = Min(s.trueStep, range);
+  s.zPath    = s.trueStep;
+  const double trueStep = s.trueStep;
+  const bool conv = !(trueStep < 1.0E-6);
+  const double tau = FastDiv(trueStep, lam);
+  const bool reg1 = conv && tau < 1.0e-16;
+  const bool reg2 = conv && !reg1 && trueStep < range * 0.05;
+  const bool reg3 = conv && !reg1 && !reg2 && (ekin < kElectronMassC2 || trueStep == range);
+  const bool reg4 = conv && !reg1 && !reg2 && !reg3;
+  const double expTau = ExpInl(reg2 ? -tau : 0.0);
+  // regime 4 (.icc:636-647): energy at the end of the step from the inverse range, lambda_1 there
+  const double rfin = Max(range - trueStep, 0.01 * range);
+  const double t1   = InvRangeInl(et, s.imc, reg4 ? rfin : range);
+  const double lt1  = LogInl(t1);
+  const int nl      = et.numLoss;
+  const double tr1  = Max(0.0, SplineLogYSDInl(nl, et.lossEGrid, et.tr1Data + 2 * nl * imat, t1, lt1, et.lossLogMinEkin, et.lossEILDelta));
+  const double lambda1 = tr1 > 0. ? FastDiv(1., tr1) : kALargeValue;
+  const bool reg34 = reg3 || reg4;
+  const double par1 = reg3 ? 1. / range : (reg4 ? (lam - lambda1) / (lam * trueStep) : 1.0);
+  const double par2 = 1. / (par1 * lam);
+  const double par3 = 1. + par2;
+  const bool powNeeded = reg4 || (reg3 && trueStep < range);
+  const double powArg  = reg3 ? 1. - trueStep / range : lambda1 / lam;
+  const double logPow  = LogInl(powNeeded ? powArg : 1.0);
+  const double powVal  = ExpInl(par3 * logPow);
+  if (reg34) {
+    s.par1 = par1;
+    s.par2 = par2;
+    s.par3 = par3;
+  }
+  double zPath = trueStep;
+  if (reg1) zPath = Min(trueStep, lam);
+  if (reg2) zPath = (tau < 1.0e-6) ? trueStep * (1. - 0.5 * tau) : lam * (1. - expTau);
+  if (reg3) {
+    zPath = 1. / (par1 * par3);
+    if (trueStep < range) zPath *= (1. - powVal);
+  }
+  if (reg4) zPath = (1. - powVal) / (par1 * par3);
+  if (conv) zPath = Min(zPath, lam);
+  s.zPath = zPath;
+  // --- the end of HowFarToMSC (.icc:155-163)
+  if (trueStep < pStepLength) {
+    s.winner = -2;
+    s.pStep  = trueStep;
+  }
+  s.gStep = Min(zPath, s.pStep);
+  return nDraw;
 }
 
-// returns true when the true -> geometrical conversion needs the inverse range regime: the track then goes to the
-// kQConvRange queue and StageHowFarMSCRange finishes it
+// uniforms `first` and `first + 1` of a track: two Philox blocks taken by every lane (one suffices when first is even)
+G4H_FN Uniform2 DrawPairAt(uint32_t k0, uint32_t k1, uint32_t id, uint32_t first) {
+  const Philox4 a = PhiloxBlockInl(k0, k1, id, first >> 1);
+  const Philox4 b = PhiloxBlockInl(k0, k1, id, (first >> 1) + 1u);
+  const double v0 = ToUniform(a.x, a.y), v1 = ToUniform(a.z, a.w), v2 = ToUniform(b.x, b.y);
+  return (first & 1u) ? Uniform2{v1, v2} : Uniform2{v0, v1};
+}
+
+// kStoreResults: also reset the result groups HowFar defines (MSC displacement)
 template <bool kStoreResults>
-G4H_FN bool StageHowFarMSC(const TablesView& tv, const G4HB200ElectronBatch& b, int64_t i, uint64_t seed) {
-  const Meta m  = LoadMeta(b.meta, i);
-  const Pair e  = LoadPair(b.ekin_logekin, i);
-  const Pair gp = LoadPair(b.gstep_pstep, i);
+G4H_FN void StageHowFarMSC(const TablesView& tv, const G4HB200ElectronBatch& b, int64_t i, uint64_t seed) {
+  const Meta m   = LoadMeta(b.meta, i);
+  const Pair e   = LoadPair(b.ekin_logekin, i);
+  const Pair gp  = LoadPair(b.gstep_pstep, i);
+  const Pair rl  = LoadPair(b.range_lambtr1, i);
+  const Pair dzs = LoadPair(b.dirz_safety, i);
+  const Pair ir  = LoadPair(b.msc_irange_dynrf, i);
+  const Pair tg  = LoadPair(b.msc_tlimmin_gauss, i);
+  const int winner = b.winner[i];
   uint32_t f = static_cast<uint32_t>(m.flags);
-  const double pStepLength = gp.b;
   if (kStoreResults) {
     // fDisplacement = 0 (.icc:127-129); the energy deposit is not a HowFar field
     const Pair ed = LoadPair(b.edep_dispx, i);
     StorePair(b.edep_dispx, i, ed.a, 0.0);
     StorePair(b.dispy_dispz, i, 0.0, 0.0);
   }
-  if (!MSCStepLimitApplies(pStepLength, e.a)) {
-    // HowFarToMSC (.icc:117-130): true = z = physical step, MSC inactive, no displacement; the rest keeps its
-    // G4HepEmMSCTrackData::ReSet() value
-    f &= ~G4HB200_F_MSC_ACTIVE;
-    StorePair(b.tstep_zpath, i, pStepLength, pStepLength);
-    StorePair(b.par12, i, -1.0, 0.0);
-    StorePair(b.par3_pad, i, 0.0, 0.0);
-    StoreMeta(b.meta, i, Meta{m.imc, static_cast<int>(f), m.id, m.draw});
-    return false;
-  }
-  const Pair rl  = LoadPair(b.range_lambtr1, i);
-  const Pair dzs = LoadPair(b.dirz_safety, i);
-  const Pair ir  = LoadPair(b.msc_irange_dynrf, i);
-  const Pair tg  = LoadPair(b.msc_tlimmin_gauss, i);
   ElectronState s;
   s.ekin = e.a; s.logEkin = e.b;
   s.imc = m.imc; s.id = m.id;
@@ -215,48 +343,26 @@ G4H_FN bool StageHowFarMSC(const TablesView& tv, const G4HB200ElectronBatch& b, 
   s.safety = dzs.b;
   s.range = rl.a; s.lambtr1 = rl.b;
   s.initialRange = ir.a; s.dynRangeFactor = ir.b; s.tlimitMin = tg.a;
-  s.pStep = pStepLength;
-  Rng rng;
-  rng.Init(seed, static_cast<uint32_t>(m.id), static_cast<uint32_t>(m.draw), (f & G4HB200_F_GAUSS_CACHED) != 0u, tg.b);
-  const bool isElectron = !s.isPositron;
-  const int theImat = G4H_LD(tv.mcImat + s.imc);
-  const int theIreg = G4H_LD(tv.mcIreg + s.imc);
-  s.trueStep  = pStepLength;
-  s.zPath     = pStepLength;
-  s.mscActive = true;
-  UMSCStepLimit(tv, s, s.ekin, theImat, theIreg, s.range, s.safety, s.onBoundary, isElectron, rng);
-  const bool rangeRegime = ConvertTrueToGeometricLengthHead(s, s.ekin, s.range);
-  f &= ~(G4HB200_F_MSC_FIRST_STEP | G4HB200_F_MSC_ACTIVE | G4HB200_F_MSC_DISPLACE | G4HB200_F_MSC_NO_SCATTER |
-         G4HB200_F_GAUSS_CACHED);
+  s.pStep = gp.b; s.gStep = gp.a; s.winner = winner;
+  bool hasGauss = (f & G4HB200_F_GAUSS_CACHED) != 0u;
+  double gauss  = tg.b;
+  const uint32_t k0 = static_cast<uint32_t>(seed), k1 = static_cast<uint32_t>(seed >> 32);
+  const Uniform2 u = DrawPairAt(k0, k1, static_cast<uint32_t>(m.id), static_cast<uint32_t>(m.draw));
+  const int nDraw = HowFarMSCCore(tv, s, hasGauss, gauss, u.a, u.b, k0, k1, static_cast<uint32_t>(m.draw));
+  f &= ~(G4HB200_F_MSC_FIRST_STEP | G4HB200_F_MSC_ACTIVE | G4HB200_F_MSC_DISPLACE | G4HB200_F_MSC_NO_SCATTER | G4HB200_F_GAUSS_CACHED);
   if (s.mscFirstStep) f |= G4HB200_F_MSC_FIRST_STEP;
-  f |= G4HB200_F_MSC_ACTIVE;
+  if (s.mscActive) f |= G4HB200_F_MSC_ACTIVE;
   if (s.mscDisplace) f |= G4HB200_F_MSC_DISPLACE;
   if (s.mscNoScatter) f |= G4HB200_F_MSC_NO_SCATTER;
-  if (rng.hasGauss) f |= G4HB200_F_GAUSS_CACHED;
+  if (hasGauss) f |= G4HB200_F_GAUSS_CACHED;
   StorePair(b.msc_irange_dynrf, i, s.initialRange, s.dynRangeFactor);
-  StorePair(b.msc_tlimmin_gauss, i, s.tlimitMin, rng.gauss);
-  StoreMeta(b.meta, i, Meta{m.imc, static_cast<int>(f), m.id, static_cast<int>(rng.draw)});
-  if (rangeRegime) {
-    // hand trueStep over (zPath = trueStep for now); gstep_pstep and the winner still hold the discrete limit
-    StorePair(b.tstep_zpath, i, s.trueStep, s.zPath);
-    return true;
-  }
-  FinishHowFarMSC(b, i, s, pStepLength, b.winner[i]);
-  return false;
-}
-
-// the inverse-range regime of the true -> geometrical conversion (.icc:636-647) for the tracks queued by StageHowFarMSC
-G4H_FN void StageHowFarMSCRange(const TablesView& tv, const G4HB200ElectronBatch& b, int64_t i) {
-  const Meta m  = LoadMeta(b.meta, i);
-  const Pair gp = LoadPair(b.gstep_pstep, i);
-  const Pair rl = LoadPair(b.range_lambtr1, i);
-  const Pair tz = LoadPair(b.tstep_zpath, i);
-  ElectronState s;
-  s.lambtr1  = rl.b;
-  s.trueStep = tz.a;
-  s.zPath    = tz.b;
-  ConvertTrueToGeometricLengthRangeRegime(tv, s, rl.a, m.imc, (static_cast<uint32_t>(m.flags) & G4HB200_F_POSITRON) == 0u);
-  FinishHowFarMSC(b, i, s, gp.b, b.winner[i]);
+  StorePair(b.msc_tlimmin_gauss, i, s.tlimitMin, gauss);
+  StoreMeta(b.meta, i, Meta{m.imc, static_cast<int>(f), m.id, m.draw + nDraw});
+  StorePair(b.tstep_zpath, i, s.trueStep, s.zPath);
+  StorePair(b.par12, i, s.par1, s.par2);
+  StorePair(b.par3_pad, i, s.par3, 0.0);
+  StorePair(b.gstep_pstep, i, s.gStep, s.pStep);
+  b.winner[i] = s.winner;
 }
 
 // ---- gamma step in two stages ----------------------------------------------------------------------------------

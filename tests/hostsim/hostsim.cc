@@ -128,11 +128,7 @@ int g4hsim_electron(const G4HB200Tables* t, G4HB200ElectronBatch* b, G4HB200Seco
 int g4hsim_electron_howfar_staged(const G4HB200Tables* t, G4HB200ElectronBatch* b, uint64_t seed) {
   const TablesView tv = MakeView(*t);
   for (int64_t i = 0; i < b->n; ++i) StageHowFarXS(tv, *b, i, seed);
-  std::vector<int64_t> queue;
-  for (int64_t i = 0; i < b->n; ++i) {
-    if (StageHowFarMSC<true>(tv, *b, i, seed)) queue.push_back(i);
-  }
-  for (int64_t i : queue) StageHowFarMSCRange(tv, *b, i);
+  for (int64_t i = 0; i < b->n; ++i) StageHowFarMSC<true>(tv, *b, i, seed);
   return 0;
 }
 

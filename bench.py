@@ -48,6 +48,8 @@ STAGE_BYTES = {
     "ElHowFarMSCKernel": (7 * 16 + 16 + 4, 8 * 16 + 16 + 4, 0),
     "ElHowFarMSCRangeKernel": (4 + 3 * 16 + 16 + 4, 4 * 16 + 4, 0),
     "ElAlongStepKernel": (11 * 16 + 16 + 4, 7 * 16, 0),
+    # fused step: 6 persistent groups + meta in; those + 3 result groups + winner + 4 hand-over groups + pre-step out
+    "ElStepHeadKernel": (6 * 16 + 16, 5 * 16 + 16 + 3 * 16 + 4 + 4 * 16 + 16, 0),
     "ElMSCSampleKernel<e->": (4 + 10 * 16 + 16 + 4, 4 * 16 + 16, 0),
     "ElMSCSampleKernel<e+>": (4 + 10 * 16 + 16 + 4, 4 * 16 + 16, 0),
     "ElFluctuationKernel": (4 + 16 + 3 * 16 + 4, 3 * 16 + 16, 0),

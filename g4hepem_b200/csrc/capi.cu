@@ -295,16 +295,16 @@ int EnsureElectronWork(G4HB200::WorkSlot& slot, int64_t n) {
 
 // pipeline stages of the e-/e+ step, in launch order (g4h_pipeline.cuh)
 enum ElStage {
-  kSHowFarXS = 0, kSHowFarMSC, kSAlongStep, kSMscEl, kSMscPos, kSFluct, kSDiscrete, kSMoller, kSBhabha, kSSB, kSRB,
+  kSHowFarXS = 0, kSHowFarMSC, kSAlongStep, kSStepHead, kSMscEl, kSMscPos, kSFluct, kSDiscrete, kSMoller, kSBhabha, kSSB, kSRB,
   kSAnnih, kSAtRest, kSGammaHead, kSGammaConversion, kSGammaCompton, kSGammaPhotoelectric,
   kNumElStages
 };
 static_assert(kNumElStages <= G4HB200_NUM_STAGES, "G4HB200_NUM_STAGES too small");
 // pipeline stage -> queue that feeds it (-1: every track of the batch)
-const int kStageQueue[G4HB200_NUM_STAGES] = {-1, -1, -1, kQMscEl, kQMscPos, kQFluct, kQDiscrete, kQMoller, kQBhabha, kQSB,
+const int kStageQueue[G4HB200_NUM_STAGES] = {-1, -1, -1, -1, kQMscEl, kQMscPos, kQFluct, kQDiscrete, kQMoller, kQBhabha, kQSB,
                                              kQRB, kQAnnih, kQAtRest, -1, kGQConversion, kGQCompton, kGQPhotoelectric};
 const char* const kStageName[G4HB200_NUM_STAGES] = {
-    "ElHowFarXSKernel", "ElHowFarMSCKernel", "ElAlongStepKernel", "ElMSCSampleKernel<e->",
+    "ElHowFarXSKernel", "ElHowFarMSCKernel", "ElAlongStepKernel", "ElStepHeadKernel", "ElMSCSampleKernel<e->",
     "ElMSCSampleKernel<e+>", "ElFluctuationKernel", "ElDiscreteKernel",
     "ElSamplerKernel<Moller>", "ElSamplerKernel<Bhabha>", "ElSamplerKernel<SeltzerBerger>", "ElSamplerKernel<RelBrem>",
     "ElSamplerKernel<Annihilation>", "ElSamplerKernel<AtRest>", "GammaHeadKernel", "GammaInteractKernel<Conversion>",
@@ -393,14 +393,17 @@ int LaunchElectronPipeline(G4HB200* h, G4HB200ElectronBatch* dev, G4HB200Seconda
   G4H_CUDA(cudaMemsetAsync(w.count, 0, kNumElQueues * sizeof(int32_t), st));
   StageTimer t{h, st};
   G4H_CUDA(t.Begin(dev->n));
-  if (kFused && (rc = LaunchHowFarStages<true>(h, dev, w, seed, st, t)) != 0) return rc;
 #define G4H_STAGE(stage, ...)       \
   G4H_CUDA(t.Before(stage));        \
   __VA_ARGS__;                      \
   G4H_CUDA(t.After(stage))
   G4HB200::WorkSlot& slot = h->slots[slotIndex];
   if ((rc = EnsureAuxStreams(slot)) != 0) return rc;
-  G4H_STAGE(kSAlongStep, ElAlongStepKernel<<<OneWave(h, ElAlongStepKernel, n), kThreadsPerBlock, 0, st>>>(h->view, *dev, w));
+  if (kFused) {
+    G4H_STAGE(kSStepHead, ElStepHeadKernel<<<OneWave(h, ElStepHeadKernel, n), kThreadsPerBlock, 0, st>>>(h->view, *dev, w, seed));
+  } else {
+    G4H_STAGE(kSAlongStep, ElAlongStepKernel<<<OneWave(h, ElAlongStepKernel, n), kThreadsPerBlock, 0, st>>>(h->view, *dev, w));
+  }
   // the two particle types are scattered side by side (disjoint queues and tracks)
   G4H_CUDA(cudaEventRecord(slot.fork, st));
   G4H_CUDA(cudaStreamWaitEvent(slot.aux[0], slot.fork, 0));

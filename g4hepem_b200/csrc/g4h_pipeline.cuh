@@ -34,6 +34,9 @@ namespace g4h {
 #ifndef G4H_MINB_MSCLIM
 #define G4H_MINB_MSCLIM 3
 #endif
+#ifndef G4H_MINB_HEAD
+#define G4H_MINB_HEAD 3
+#endif
 #ifndef G4H_MINB_ALONG
 #define G4H_MINB_ALONG 3
 #endif
@@ -76,6 +79,20 @@ ElAlongStepKernel(const __grid_constant__ TablesView tv, const __grid_constant__
   for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < nRound; i += stride) {
     const int route = i < b.n ? StageAlongStep(tv, b, w.prestep, i) : -1;
     // kQFluct, kQDiscrete, kQAtRest, kQMscEl, kQMscPos are queues 0..4
+    RouteToQueues<5>(cc, route, static_cast<int32_t>(i), w.queue, w.count);
+  }
+}
+
+// ---- the fused step: HowFar + along-step part of Perform for every track (g4h_stages.cuh) ---------------------------------
+__global__ void __launch_bounds__(kThreadsPerBlock, G4H_MINB_HEAD)
+ElStepHeadKernel(const __grid_constant__ TablesView tv, const __grid_constant__ G4HB200ElectronBatch b,
+                 const __grid_constant__ ElectronWork w, uint64_t seed) {
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  const int64_t nRound = RoundUpToCta(b.n);
+  __shared__ CtaCounters<5> cc;
+  cc.Init();
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < nRound; i += stride) {
+    const int route = i < b.n ? StageStepHead(tv, b, w.prestep, i, seed) : -1;
     RouteToQueues<5>(cc, route, static_cast<int32_t>(i), w.queue, w.count);
   }
 }

@@ -365,6 +365,91 @@ G4H_FN void StageHowFarMSC(const TablesView& tv, const G4HB200ElectronBatch& b, 
   b.winner[i] = s.winner;
 }
 
+// ---- the fused step: HowFar and the along-step part of Perform in one pass over the track -------------------------------
+// g4hb200_electron_step: geometry accepts the proposed step, so nothing happens between HowFar and Perform and the
+// hand-over state (mean free paths, range, MSC step data) can stay in registers: HowFarXS + HowFarMSC + AlongStep
+// as three kernels moved 670 MB per 1M tracks through HBM and were bound by memory latency, the fused stage reads
+// the seven persistent groups and writes what the queue kernels behind it need.  par12 / par3_pad are not written.
+// Draws come from one DrawWindow (at most four for the interaction lengths + two for the Gaussian).
+G4H_FN int ResampleNumIALeftWindow(double* nIA, const DrawWindow& dw) {
+  int count = 0;
+  double u[4];
+#pragma unroll
+  for (int ip = 0; ip < 4; ++ip) {
+    const bool need = nIA[ip] <= 0.;
+    u[ip] = need ? (count == 0 ? dw.u[0] : count == 1 ? dw.u[1] : count == 2 ? dw.u[2] : dw.u[3]) : 1.0;
+    count += need ? 1 : 0;
+  }
+  const double l0 = LogInl(u[0]);
+  const double l1 = LogInl(u[1]);
+  const double l2 = LogInl(u[2]);
+  const double l3 = LogInl(u[3]);
+  if (nIA[0] <= 0.) nIA[0] = -l0;
+  if (nIA[1] <= 0.) nIA[1] = -l1;
+  if (nIA[2] <= 0.) nIA[2] = -l2;
+  if (nIA[3] <= 0.) nIA[3] = -l3;
+  return count;
+}
+
+// returns the queue the track goes to next (kQFluct, kQDiscrete, kQAtRest, kQMscEl, kQMscPos) or -1
+G4H_FN int StageStepHead(const TablesView& tv, const G4HB200ElectronBatch& b, double* prestep, int64_t i, uint64_t seed) {
+  const Meta m   = LoadMeta(b.meta, i);
+  const Pair e   = LoadPair(b.ekin_logekin, i);
+  const Pair n01 = LoadPair(b.nia01, i);
+  const Pair n23 = LoadPair(b.nia23, i);
+  const Pair dzs = LoadPair(b.dirz_safety, i);
+  const Pair ir  = LoadPair(b.msc_irange_dynrf, i);
+  const Pair tg  = LoadPair(b.msc_tlimmin_gauss, i);
+  uint32_t f = static_cast<uint32_t>(m.flags);
+  ElectronState s;
+  s.ekin = e.a; s.logEkin = e.b;
+  s.imc = m.imc; s.id = m.id;
+  s.isPositron   = (f & G4HB200_F_POSITRON) != 0u;
+  s.onBoundary   = (f & G4HB200_F_ON_BOUNDARY) != 0u;
+  s.mscFirstStep = (f & G4HB200_F_MSC_FIRST_STEP) != 0u;
+  s.mscDisplace  = (f & G4HB200_F_MSC_DISPLACE) != 0u;
+  s.mscNoScatter = (f & G4HB200_F_MSC_NO_SCATTER) != 0u;
+  s.safety = dzs.b;
+  s.nIA[0] = n01.a; s.nIA[1] = n01.b; s.nIA[2] = n23.a; s.nIA[3] = n23.b;
+  s.initialRange = ir.a; s.dynRangeFactor = ir.b; s.tlimitMin = tg.a;
+  s.preStepEkin = 0.0; s.preStepLogEkin = 0.0;
+  bool hasGauss = (f & G4HB200_F_GAUSS_CACHED) != 0u;
+  double gauss  = tg.b;
+  DrawWindow dw;
+  dw.Init(seed, static_cast<uint32_t>(m.id), static_cast<uint32_t>(m.draw));
+  // HowFar (.icc:35-45): interaction lengths, discrete step limit, MSC step limit
+  const int nXS = ResampleNumIALeftWindow(s.nIA, dw);
+  const double lam = HowFarToDiscreteInteractionILP(tv, s);
+  s.lambtr1 = MSCStepLimitApplies(s.pStep, s.ekin) ? lam : 0.0;
+  const double uA = nXS == 0 ? dw.u[0] : nXS == 1 ? dw.u[1] : nXS == 2 ? dw.u[2] : nXS == 3 ? dw.u[3] : dw.u[4];
+  const double uB = nXS == 0 ? dw.u[1] : nXS == 1 ? dw.u[2] : nXS == 2 ? dw.u[3] : nXS == 3 ? dw.u[4] : dw.Sixth();
+  const int nMSC = HowFarMSCCore(tv, s, hasGauss, gauss, uA, uB, dw.k0, dw.k1, static_cast<uint32_t>(m.draw + nXS));
+  // geometry accepts the step: fGStepLength and fOnBoundary stay; Perform, along-step part
+  const int route = AlongStepCore(tv, s);
+  f &= ~(G4HB200_F_MSC_FIRST_STEP | G4HB200_F_MSC_ACTIVE | G4HB200_F_MSC_DISPLACE | G4HB200_F_MSC_NO_SCATTER | G4HB200_F_GAUSS_CACHED);
+  if (s.mscFirstStep) f |= G4HB200_F_MSC_FIRST_STEP;
+  if (s.mscActive) f |= G4HB200_F_MSC_ACTIVE;
+  if (s.mscDisplace) f |= G4HB200_F_MSC_DISPLACE;
+  if (s.mscNoScatter) f |= G4HB200_F_MSC_NO_SCATTER;
+  if (hasGauss) f |= G4HB200_F_GAUSS_CACHED;
+  StorePair(b.ekin_logekin, i, s.ekin, s.logEkin);
+  StorePair(b.nia01, i, s.nIA[0], s.nIA[1]);
+  StorePair(b.nia23, i, s.nIA[2], s.nIA[3]);
+  StorePair(b.msc_irange_dynrf, i, s.initialRange, s.dynRangeFactor);
+  StorePair(b.msc_tlimmin_gauss, i, s.tlimitMin, gauss);
+  StoreMeta(b.meta, i, Meta{m.imc, static_cast<int>(f), m.id, m.draw + nXS + nMSC});
+  StorePair(b.gstep_pstep, i, s.gStep, s.pStep);
+  StorePair(b.edep_dispx, i, s.edep, 0.0);  // fDisplacement = 0 (.icc:127-129)
+  StorePair(b.dispy_dispz, i, 0.0, 0.0);
+  b.winner[i] = s.winner;
+  StorePair(b.mfp01, i, s.mfp[0], s.mfp[1]);
+  StorePair(b.mfp23, i, s.mfp[2], s.mfp[3]);
+  StorePair(b.range_lambtr1, i, s.range, s.lambtr1);
+  StorePair(b.tstep_zpath, i, s.trueStep, s.zPath);
+  StorePair(prestep, i, s.preStepEkin, s.preStepLogEkin);
+  return route == -2 ? -1 : route;
+}
+
 // ---- gamma step in two stages ----------------------------------------------------------------------------------
 //   StageGammaHead       HowFar (G4HepEmGammaManager.icc:27-48; kMode 2) + SelectInteraction (.icc:173-219) +
 //                        UpdateNumIALeft and the head of Perform (.icc:54-76): returns the process that interacts

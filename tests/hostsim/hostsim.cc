@@ -133,12 +133,14 @@ int g4hsim_electron_howfar_staged(const G4HB200Tables* t, G4HB200ElectronBatch* 
 }
 
 // the staged Perform (g4h_perform_stages.cuh), stage after stage over the queues like the kernels do
-int g4hsim_electron_perform_staged(const G4HB200Tables* t, G4HB200ElectronBatch* b, G4HB200SecondaryQueue* q, uint64_t seed) {
+// fused != 0: the fused step (StageStepHead instead of HowFar + StageAlongStep)
+int g4hsim_electron_perform_staged(const G4HB200Tables* t, G4HB200ElectronBatch* b, G4HB200SecondaryQueue* q, uint64_t seed,
+                                   int fused) {
   const TablesView tv = MakeView(*t);
   std::vector<double> prestep(2 * static_cast<size_t>(b->n) + 2);
   std::vector<int64_t> queue[kNumElQueues];
   for (int64_t i = 0; i < b->n; ++i) {
-    const int r = StageAlongStep(tv, *b, prestep.data(), i);
+    const int r = fused ? StageStepHead(tv, *b, prestep.data(), i, seed) : StageAlongStep(tv, *b, prestep.data(), i);
     if (r >= 0) queue[r].push_back(i);
   }
   const double cbeta1 = MscCBeta1();

@@ -82,7 +82,11 @@ class HostSim:
 
     def electron_perform_staged(self, b, sec, seed):
         s, q = b.as_struct(), sec.as_struct()
-        self.lib.g4hsim_electron_perform_staged(self.t, C.byref(s), C.byref(q), C.c_uint64(seed))
+        self.lib.g4hsim_electron_perform_staged(self.t, C.byref(s), C.byref(q), C.c_uint64(seed), 0)
+
+    def electron_step_staged(self, b, sec, seed):
+        s, q = b.as_struct(), sec.as_struct()
+        self.lib.g4hsim_electron_perform_staged(self.t, C.byref(s), C.byref(q), C.c_uint64(seed), 1)
 
     def electron_step(self, b, sec, seed):
         self._run(self.lib.g4hsim_electron, b, sec, seed, 2)

@@ -73,3 +73,21 @@ def test_gamma_step(sim, reference, flat_tables, staged):
     rep = compare.compare_gamma_batches(g, h)
     assert compare.total_bad(rep) == 0, compare.format_report(rep, True)
     assert compare.total_bad(compare.compare_secondaries(qa, qb)) == 0
+
+
+def test_electron_fused_step_staged(sim, reference, flat_tables):
+    """StageStepHead (HowFar + along-step in one pass) + the queue stages over consecutive steps."""
+    n = 30000
+    a = batches.make_electron_batch(n, flat_tables.num_matcut, seed=9)
+    b = a.copy()
+    for _ in range(4):
+        qa, qb = batches.SecondaryHostQueue(2 * n), batches.SecondaryHostQueue(2 * n)
+        reference.electron_step(a, qa, 2026, 4)
+        sim.electron_step_staged(b, qb, 2026)
+        rep = compare.compare_electron_batches(a, b, handover=False)
+        assert compare.total_bad(rep) == 0, compare.format_report(rep, True)
+        assert compare.total_bad(compare.compare_secondaries(qa, qb)) == 0
+        dead = a.ekin_logekin[:, 0] <= 0
+        for x in (a, b):
+            x.ekin_logekin[dead, 0] = 1.0
+            x.ekin_logekin[dead, 1] = 100.0

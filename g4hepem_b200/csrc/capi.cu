@@ -123,6 +123,10 @@ struct G4HB200 {
   int32_t* chunkCounters = nullptr;  // device, [kMaxChunks]
   static constexpr int kMaxChunks = 256;
   bool monolith = false;  // G4HB200_MONOLITH=1: the one-kernel-per-step variant (kept for A/B measurements)
+  // device batches of at least this many tracks run as two half-batch pipelines side by side (G4HB200_SPLIT_MIN)
+  int64_t splitThreshold = 1 << 18;
+  int splitParts = 2;  // G4HB200_SPLIT_PARTS, at most kNumSlots
+  cudaEvent_t splitFork = nullptr, splitJoin[4] = {};
   // per-kernel timing (g4hb200_set_kernel_timing): one event row per timed pipeline call
   bool timing = false;
   struct TimedCall {
@@ -498,6 +502,64 @@ int LaunchGammaPipeline(G4HB200* h, G4HB200GammaBatch* dev, G4HB200SecondaryQueu
   return 0;
 }
 
+// A sub-range of a batch (same struct, pointers advanced).
+G4HB200ElectronBatch ElectronBatchView(const G4HB200ElectronBatch& full, int64_t lo, int64_t len) {
+  G4HB200ElectronBatch v = full;
+  double** g[16];
+  ElectronDoubleGroups(&v, g);
+  for (int k = 0; k < 16; ++k) if (*g[k] != nullptr) *g[k] += 2 * lo;
+  if (v.meta != nullptr) v.meta += 4 * lo;
+  if (v.winner != nullptr) v.winner += lo;
+  v.n = len;
+  return v;
+}
+
+// The pipeline of a large device batch as a few part-batch pipelines side by side (the caller's stream and internal
+// streams, fork / join by events).  The queue kernels at the end of a pipeline (discrete head, final state
+// samplers: 20-35 % of the issue slots, bound by gather latency and rejection loops) leave most of the machine idle;
+// with two halves in flight they run next to the other half's arithmetic-bound head / MSC / fluctuation kernels.
+// Tracks are independent and the uniform stream is keyed per track, so the result does not depend on the split.
+template <bool kFused>
+int LaunchElectronPipelineHalves(G4HB200* h, G4HB200ElectronBatch* dev, G4HB200SecondaryQueue* sec, uint64_t seed, void* stream) {
+  int rc = CheckHandle(h);
+  if (rc != 0) return rc;
+  if (dev == nullptr || sec == nullptr || dev->n < h->splitThreshold || h->timing || h->splitParts < 2) {
+    return LaunchElectronPipeline<kFused>(h, dev, sec, seed, stream);
+  }
+  if (dev->n > 0x7fffffff) return Fail(G4HB200_EINVAL, "batch too large (track indices are 32 bit)");
+  const int parts = h->splitParts;
+  for (int p = 1; p < parts; ++p) {
+    G4HB200::WorkSlot& other = h->slots[p];
+    if (other.stream == nullptr) {
+      G4H_CUDA(cudaStreamCreateWithFlags(&other.stream, cudaStreamNonBlocking));
+      G4H_CUDA(cudaEventCreateWithFlags(&other.counted, cudaEventDisableTiming));
+    }
+  }
+  if (h->splitFork == nullptr) {
+    G4H_CUDA(cudaEventCreateWithFlags(&h->splitFork, cudaEventDisableTiming));
+    for (auto& e : h->splitJoin) G4H_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+  }
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int64_t per = ((dev->n / parts + kThreadsPerBlock - 1) / kThreadsPerBlock) * kThreadsPerBlock;
+  G4H_CUDA(cudaEventRecord(h->splitFork, st));
+  for (int p = 1; p < parts; ++p) G4H_CUDA(cudaStreamWaitEvent(h->slots[p].stream, h->splitFork, 0));
+  for (int p = 0; p < parts; ++p) {
+    const int64_t lo = p * per;
+    if (lo >= dev->n) break;
+    const int64_t len = (p == parts - 1 || lo + per > dev->n) ? dev->n - lo : per;
+    G4HB200ElectronBatch part = ElectronBatchView(*dev, lo, len);
+    G4HB200SecondaryQueue q = *sec;
+    q.parent_base = sec->parent_base + static_cast<int32_t>(lo);
+    cudaStream_t ps = p == 0 ? st : h->slots[p].stream;
+    if ((rc = LaunchElectronPipeline<kFused>(h, &part, &q, seed, ps, p)) != 0) return rc;
+  }
+  for (int p = 1; p < parts; ++p) {
+    G4H_CUDA(cudaEventRecord(h->splitJoin[p], h->slots[p].stream));
+    G4H_CUDA(cudaStreamWaitEvent(st, h->splitJoin[p], 0));
+  }
+  return 0;
+}
+
 }  // namespace
 
 extern "C" {
@@ -592,6 +654,11 @@ int g4hb200_create(const G4HB200Tables* tables, int device, G4HB200** out) {
   {
     const char* mono = std::getenv("G4HB200_MONOLITH");
     h->monolith = mono != nullptr && mono[0] == '1';
+    if (const char* sp = std::getenv("G4HB200_SPLIT_MIN")) h->splitThreshold = std::atoll(sp);
+    if (const char* sp = std::getenv("G4HB200_SPLIT_PARTS")) {
+      const int v = std::atoi(sp);
+      if (v >= 1 && v <= G4HB200::kNumSlots) h->splitParts = v;
+    }
   }
   G4H_CUDA(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
   std::memset(&h->elDev, 0, sizeof(h->elDev));
@@ -615,6 +682,10 @@ int g4hb200_destroy(G4HB200* h) {
     for (auto& a : slot.aux) if (a != nullptr) cudaStreamDestroy(a);
     for (auto& e : slot.join) if (e != nullptr) cudaEventDestroy(e);
     if (slot.fork != nullptr) cudaEventDestroy(slot.fork);
+  }
+  if (h->splitFork != nullptr) {
+    cudaEventDestroy(h->splitFork);
+    for (auto& e : h->splitJoin) cudaEventDestroy(e);
   }
   if (h->pinnedCounts != nullptr) cudaFreeHost(h->pinnedCounts);
   if (h->chunkCounters != nullptr) cudaFree(h->chunkCounters);
@@ -862,11 +933,11 @@ int g4hb200_electron_howfar(G4HB200* h, G4HB200ElectronBatch* dev, uint64_t seed
 }
 int g4hb200_electron_perform(G4HB200* h, G4HB200ElectronBatch* dev, G4HB200SecondaryQueue* sec, uint64_t seed, void* stream) {
   if (h != nullptr && h->monolith) return LaunchElectron<1>(h, dev, sec, seed, stream);
-  return LaunchElectronPipeline<false>(h, dev, sec, seed, stream);
+  return LaunchElectronPipelineHalves<false>(h, dev, sec, seed, stream);
 }
 int g4hb200_electron_step(G4HB200* h, G4HB200ElectronBatch* dev, G4HB200SecondaryQueue* sec, uint64_t seed, void* stream) {
   if (h != nullptr && h->monolith) return LaunchElectron<2>(h, dev, sec, seed, stream);
-  return LaunchElectronPipeline<true>(h, dev, sec, seed, stream);
+  return LaunchElectronPipelineHalves<true>(h, dev, sec, seed, stream);
 }
 int g4hb200_gamma_howfar(G4HB200* h, G4HB200GammaBatch* dev, uint64_t seed, void* stream) {
   return LaunchGamma<0>(h, dev, nullptr, seed, stream);
@@ -929,16 +1000,7 @@ int g4hb200_electron_step_host(G4HB200* h, G4HB200ElectronBatch* host, G4HB200Se
   G4H_CUDA(cudaMemsetAsync(h->chunkCounters, 0, numChunks * sizeof(int32_t), h->slots[0].stream));
   G4H_CUDA(cudaStreamSynchronize(h->slots[0].stream));
   std::vector<cudaEvent_t> counted(numChunks);
-  auto view = [](const G4HB200ElectronBatch& full, int64_t lo, int64_t len) {
-    G4HB200ElectronBatch v = full;
-    double** g[16];
-    ElectronDoubleGroups(&v, g);
-    for (int k = 0; k < 16; ++k) if (*g[k] != nullptr) *g[k] += 2 * lo;
-    if (v.meta != nullptr) v.meta += 4 * lo;
-    if (v.winner != nullptr) v.winner += lo;
-    v.n = len;
-    return v;
-  };
+  auto view = ElectronBatchView;
   for (int c = 0; c < numChunks; ++c) {
     G4HB200::WorkSlot& slot = h->slots[c % G4HB200::kNumSlots];
     const int64_t lo = c * chunk, len = (lo + chunk <= n) ? chunk : n - lo;

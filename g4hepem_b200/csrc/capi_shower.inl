@@ -151,6 +151,10 @@ int RunStepLoop(G4HB200* h, const G4HB200SlabGeometry* geom, int64_t numPrimarie
   // size the pipelines' workspaces once (they grow on demand otherwise: a reallocation per iteration while the
   // shower develops)
   if ((rc = EnsureElectronWork(h->slots[0], capacity)) != 0) return fail(rc);
+  // large populations run as part-batch pipelines side by side (LaunchElectronPipelineHalves): their slots too
+  for (int p = 1; p < h->splitParts; ++p) {
+    if ((rc = EnsureElectronWork(h->slots[p], capacity / h->splitParts + 2 * kThreadsPerBlock)) != 0) return fail(rc);
+  }
   if ((rc = EnsureElectronWork(h->gmSlot, capacity)) != 0) return fail(rc);
   cudaStream_t st = h->stream;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;

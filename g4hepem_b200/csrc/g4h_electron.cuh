@@ -594,8 +594,9 @@ G4H_FN double SampleEnergyLossFluctuation(double tcut, double excEner, double me
       const double w = (tcut - w3) / tcut;
       const int nnb  = rng.Poisson(p3);
       // the reference draws in blocks of 8 + a tail; the stream is consumed one uniform per term either way
+      // 1 - w u is in [w3 / tcut, 1]: the division is in the safe range of FastDiv
       for (int i = 0; i < nnb; ++i) {
-        eloss += w3 / (1. - w * rng.Flat());
+        eloss += FastDiv(w3, 1. - w * rng.Flat());
       }
     }
   }

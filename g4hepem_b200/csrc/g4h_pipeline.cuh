@@ -212,6 +212,10 @@ GammaInteractKernel(const __grid_constant__ TablesView tv, const __grid_constant
   const int nRound = static_cast<int>(RoundUpToCta(cnt));
   const int stride = gridDim.x * blockDim.x;
   __shared__ CtaCounters<1> cc;
+  // draws per track (tools, reference run): conversion 11-12 (p90), Compton 4-7, photoelectric 1 (median; most
+  // photons are absorbed below the K edge without an electron) .. 9 (p90)
+  constexpr uint32_t kSlots = kProc == kGQCompton ? G4H_WINDOW_SAMPLER : (kProc == kGQConversion ? 2 * G4H_WINDOW_SAMPLER : 4);
+  __shared__ double window[kSlots * kThreadsPerBlock];
   cc.Init();
   for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < nRound; q += stride) {
     Secondaries sec;
@@ -220,7 +224,7 @@ GammaInteractKernel(const __grid_constant__ TablesView tv, const __grid_constant
     int id = 0;
     if (q < cnt) {
       i = w.queue[kProc][q];
-      StageGammaInteract<kProc>(tv, b, i, seed, sec, id);
+      StageGammaInteract<kProc>(tv, b, i, seed, sec, id, window + threadIdx.x, kThreadsPerBlock, kSlots);
     }
     AppendSecondaries(cc, sq, sec, id, i);
   }

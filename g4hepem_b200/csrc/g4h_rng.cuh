@@ -137,8 +137,26 @@ struct Rng {
   // fill `slots` (even) window entries starting at the block that holds the next draw; call right after Init
   G4H_MFN void FillWindow(double* window, uint32_t stride, uint32_t slots) {
     const uint32_t blk0 = draw >> 1;
+    uint32_t k = 0;
+    // four blocks at a time, inlined: the ten rounds of one block are a dependent chain of integer multiplies
 #pragma unroll 1
-    for (uint32_t k = 0; k < slots; k += 2) {
+    for (; k + 8u <= slots; k += 8u) {
+      const uint32_t b = blk0 + (k >> 1);
+      const Philox4 p0 = PhiloxBlockInl(k0, k1, id, b);
+      const Philox4 p1 = PhiloxBlockInl(k0, k1, id, b + 1u);
+      const Philox4 p2 = PhiloxBlockInl(k0, k1, id, b + 2u);
+      const Philox4 p3 = PhiloxBlockInl(k0, k1, id, b + 3u);
+      window[k * stride]        = ToUniform(p0.x, p0.y);
+      window[(k + 1u) * stride] = ToUniform(p0.z, p0.w);
+      window[(k + 2u) * stride] = ToUniform(p1.x, p1.y);
+      window[(k + 3u) * stride] = ToUniform(p1.z, p1.w);
+      window[(k + 4u) * stride] = ToUniform(p2.x, p2.y);
+      window[(k + 5u) * stride] = ToUniform(p2.z, p2.w);
+      window[(k + 6u) * stride] = ToUniform(p3.x, p3.y);
+      window[(k + 7u) * stride] = ToUniform(p3.z, p3.w);
+    }
+#pragma unroll 1
+    for (; k < slots; k += 2u) {
       const Uniform2 u = UniformPair(k0, k1, id, blk0 + (k >> 1));
       window[k * stride]        = u.a;
       window[(k + 1u) * stride] = u.b;
@@ -197,7 +215,7 @@ struct Rng {
       double poissonSum = poissonValue;
       while (poissonSum <= position) {
         ++number;
-        poissonValue *= mean / number;
+        poissonValue *= FastDiv(mean, static_cast<double>(number));  // mean in (0, 16], number a small integer
         poissonSum += poissonValue;
       }
       return number;

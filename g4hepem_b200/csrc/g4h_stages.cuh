@@ -488,7 +488,7 @@ G4H_FN int StageGammaHead(const TablesView& tv, const G4HB200GammaBatch& b, int6
 
 template <int kProc>
 G4H_FN void StageGammaInteract(const TablesView& tv, const G4HB200GammaBatch& b, int64_t i, uint64_t seed, Secondaries& sec,
-                               int& id) {
+                               int& id, double* window = nullptr, uint32_t windowStride = 0u, uint32_t windowSlots = 0u) {
   const Meta m   = LoadMeta(b.meta, i);
   const Pair e   = LoadPair(b.ekin_logekin, i);
   const Pair dxy = LoadPair(b.dirx_diry, i);
@@ -502,6 +502,7 @@ G4H_FN void StageGammaInteract(const TablesView& tv, const G4HB200GammaBatch& b,
   id = m.id;
   Rng rng;
   rng.Init(seed, static_cast<uint32_t>(m.id), static_cast<uint32_t>(m.draw), false, 0.0);
+  if (windowSlots != 0u) rng.FillWindow(window, windowStride, windowSlots);
   if (kProc == 0) PerformConversion(tv, s, rng, sec);
   if (kProc == 1) PerformCompton(s, rng, sec);
   if (kProc == 2) PerformPhotoelectric(tv, s, rng, sec);

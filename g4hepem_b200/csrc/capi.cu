@@ -119,6 +119,7 @@ struct G4HB200 {
   static constexpr int kNumSlots = 4;
   WorkSlot slots[kNumSlots];         // slot 0 also serves the device-batch entry points
   WorkSlot gmSlot;                   // queues of the gamma pipeline
+  WorkSlot gmSlot2;                  // ... of the second part-batch (LaunchGammaPipelineHalves)
   int32_t* pinnedCounts = nullptr;   // [kMaxChunks] secondary counts of the chunks of a host call
   int32_t* chunkCounters = nullptr;  // device, [kMaxChunks]
   static constexpr int kMaxChunks = 256;
@@ -460,14 +461,15 @@ int EnsureAuxStreams(G4HB200::WorkSlot& slot) {
 // G4HepEmGammaManager::[HowFar +] SelectInteraction + Perform as a pipeline: head over every track, then the three
 // final state samplers side by side over their queues (g4h_pipeline.cuh); kMode 1: Perform, 2: fused step
 template <int kMode>
-int LaunchGammaPipeline(G4HB200* h, G4HB200GammaBatch* dev, G4HB200SecondaryQueue* sec, uint64_t seed, void* stream) {
+int LaunchGammaPipeline(G4HB200* h, G4HB200GammaBatch* dev, G4HB200SecondaryQueue* sec, uint64_t seed, void* stream,
+                        bool secondSlot = false) {
   int rc = CheckHandle(h);
   if (rc != 0) return rc;
   if (dev == nullptr || dev->n < 0) return Fail(G4HB200_EINVAL, "bad gamma batch");
   if (sec == nullptr) return Fail(G4HB200_EINVAL, "secondary queue required");
   if (dev->n == 0) return 0;
   if (dev->n > 0x7fffffff) return Fail(G4HB200_EINVAL, "batch too large (track indices are 32 bit)");
-  G4HB200::WorkSlot& slot = h->gmSlot;
+  G4HB200::WorkSlot& slot = secondSlot ? h->gmSlot2 : h->gmSlot;
   if ((rc = EnsureElectronWork(slot, dev->n)) != 0) return rc;
   if ((rc = EnsureAuxStreams(slot)) != 0) return rc;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
@@ -557,6 +559,50 @@ int LaunchElectronPipelineHalves(G4HB200* h, G4HB200ElectronBatch* dev, G4HB200S
     G4H_CUDA(cudaEventRecord(h->splitJoin[p], h->slots[p].stream));
     G4H_CUDA(cudaStreamWaitEvent(st, h->splitJoin[p], 0));
   }
+  return 0;
+}
+
+G4HB200GammaBatch GammaBatchView(const G4HB200GammaBatch& full, int64_t lo, int64_t len) {
+  G4HB200GammaBatch v = full;
+  double** g[5];
+  GammaDoubleGroups(&v, g);
+  for (int k = 0; k < 5; ++k) if (*g[k] != nullptr) *g[k] += 2 * lo;
+  if (v.meta != nullptr) v.meta += 4 * lo;
+  if (v.winner != nullptr) v.winner += lo;
+  v.n = len;
+  return v;
+}
+
+// the gamma pipeline of a large device batch as two half-batch pipelines side by side (see the e-/e+ one above)
+template <int kMode>
+int LaunchGammaPipelineHalves(G4HB200* h, G4HB200GammaBatch* dev, G4HB200SecondaryQueue* sec, uint64_t seed, void* stream) {
+  int rc = CheckHandle(h);
+  if (rc != 0) return rc;
+  if (dev == nullptr || sec == nullptr || dev->n < h->splitThreshold || h->timing || h->splitParts < 2) {
+    return LaunchGammaPipeline<kMode>(h, dev, sec, seed, stream);
+  }
+  if (dev->n > 0x7fffffff) return Fail(G4HB200_EINVAL, "batch too large (track indices are 32 bit)");
+  G4HB200::WorkSlot& other = h->gmSlot2;
+  if (other.stream == nullptr) {
+    G4H_CUDA(cudaStreamCreateWithFlags(&other.stream, cudaStreamNonBlocking));
+    G4H_CUDA(cudaEventCreateWithFlags(&other.counted, cudaEventDisableTiming));
+  }
+  if (h->splitFork == nullptr) {
+    G4H_CUDA(cudaEventCreateWithFlags(&h->splitFork, cudaEventDisableTiming));
+    for (auto& e : h->splitJoin) G4H_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+  }
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int64_t n0 = ((dev->n / 2 + kThreadsPerBlock - 1) / kThreadsPerBlock) * kThreadsPerBlock;
+  G4HB200GammaBatch first  = GammaBatchView(*dev, 0, n0);
+  G4HB200GammaBatch second = GammaBatchView(*dev, n0, dev->n - n0);
+  G4HB200SecondaryQueue q1 = *sec;
+  q1.parent_base = sec->parent_base + static_cast<int32_t>(n0);
+  G4H_CUDA(cudaEventRecord(h->splitFork, st));
+  G4H_CUDA(cudaStreamWaitEvent(other.stream, h->splitFork, 0));
+  if ((rc = LaunchGammaPipeline<kMode>(h, &first, sec, seed, st, false)) != 0) return rc;
+  if ((rc = LaunchGammaPipeline<kMode>(h, &second, &q1, seed, other.stream, true)) != 0) return rc;
+  G4H_CUDA(cudaEventRecord(h->splitJoin[0], other.stream));
+  G4H_CUDA(cudaStreamWaitEvent(st, h->splitJoin[0], 0));
   return 0;
 }
 
@@ -674,7 +720,7 @@ int g4hb200_destroy(G4HB200* h) {
   if (h->elCap > 0) g4hb200_electron_batch_free(h, &h->elDev);
   if (h->gmCap > 0) g4hb200_gamma_batch_free(h, &h->gmDev);
   if (h->secCap > 0) g4hb200_secondary_queue_free(h, &h->secDev);
-  for (G4HB200::WorkSlot* sp : {&h->slots[0], &h->slots[1], &h->slots[2], &h->slots[3], &h->gmSlot}) {
+  for (G4HB200::WorkSlot* sp : {&h->slots[0], &h->slots[1], &h->slots[2], &h->slots[3], &h->gmSlot, &h->gmSlot2}) {
     G4HB200::WorkSlot& slot = *sp;
     if (slot.mem != nullptr) cudaFree(slot.mem);
     if (slot.stream != nullptr) cudaStreamDestroy(slot.stream);
@@ -944,11 +990,11 @@ int g4hb200_gamma_howfar(G4HB200* h, G4HB200GammaBatch* dev, uint64_t seed, void
 }
 int g4hb200_gamma_perform(G4HB200* h, G4HB200GammaBatch* dev, G4HB200SecondaryQueue* sec, uint64_t seed, void* stream) {
   if (h != nullptr && h->monolith) return LaunchGamma<1>(h, dev, sec, seed, stream);
-  return LaunchGammaPipeline<1>(h, dev, sec, seed, stream);
+  return LaunchGammaPipelineHalves<1>(h, dev, sec, seed, stream);
 }
 int g4hb200_gamma_step(G4HB200* h, G4HB200GammaBatch* dev, G4HB200SecondaryQueue* sec, uint64_t seed, void* stream) {
   if (h != nullptr && h->monolith) return LaunchGamma<2>(h, dev, sec, seed, stream);
-  return LaunchGammaPipeline<2>(h, dev, sec, seed, stream);
+  return LaunchGammaPipelineHalves<2>(h, dev, sec, seed, stream);
 }
 
 // Host buffers in, host buffers out.  The batch is cut into chunks that travel on kNumSlots streams: while chunk c

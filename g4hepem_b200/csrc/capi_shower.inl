@@ -156,6 +156,7 @@ int RunStepLoop(G4HB200* h, const G4HB200SlabGeometry* geom, int64_t numPrimarie
     if ((rc = EnsureElectronWork(h->slots[p], capacity / h->splitParts + 2 * kThreadsPerBlock)) != 0) return fail(rc);
   }
   if ((rc = EnsureElectronWork(h->gmSlot, capacity)) != 0) return fail(rc);
+  if (h->splitParts > 1 && (rc = EnsureElectronWork(h->gmSlot2, capacity / 2 + 2 * kThreadsPerBlock)) != 0) return fail(rc);
   cudaStream_t st = h->stream;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   cudaEventCreate(&ev0);

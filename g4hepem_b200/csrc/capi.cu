@@ -409,34 +409,47 @@ int LaunchElectronPipeline(G4HB200* h, G4HB200ElectronBatch* dev, G4HB200Seconda
   } else {
     G4H_STAGE(kSAlongStep, ElAlongStepKernel<<<OneWave(h, ElAlongStepKernel, n), kThreadsPerBlock, 0, st>>>(h->view, *dev, w));
   }
-  // the two particle types are scattered side by side (disjoint queues and tracks)
-  G4H_CUDA(cudaEventRecord(slot.fork, st));
-  G4H_CUDA(cudaStreamWaitEvent(slot.aux[0], slot.fork, 0));
+  // the two particle types are scattered side by side (disjoint queues and tracks).  With per-kernel timing on,
+  // every kernel runs alone on the caller's stream instead: the CUDA-event durations are then those of the kernels
+  // themselves (comparable with an ncu launch list), not of kernels waiting for each other's SMs.
+  const bool alone = t.tc != nullptr;
+  cudaStream_t side[G4HB200::WorkSlot::kNumAux];
+  for (int k = 0; k < G4HB200::WorkSlot::kNumAux; ++k) side[k] = alone ? st : slot.aux[k];
+  if (!alone) {
+    G4H_CUDA(cudaEventRecord(slot.fork, st));
+    G4H_CUDA(cudaStreamWaitEvent(slot.aux[0], slot.fork, 0));
+  }
   G4H_STAGE(kSMscEl, ElMSCSampleKernel<false><<<OneWave(h, ElMSCSampleKernel<false>, n), kThreadsPerBlock, 0, st>>>(h->view, *dev, w, seed));
-  G4H_CUDA(t.Before(kSMscPos, slot.aux[0]));
-  ElMSCSampleKernel<true><<<OneWave(h, ElMSCSampleKernel<true>, n), kThreadsPerBlock, 0, slot.aux[0]>>>(h->view, *dev, w, seed);
-  G4H_CUDA(t.After(kSMscPos, slot.aux[0]));
-  G4H_CUDA(cudaEventRecord(slot.join[0], slot.aux[0]));
-  G4H_CUDA(cudaStreamWaitEvent(st, slot.join[0], 0));
+  G4H_CUDA(t.Before(kSMscPos, side[0]));
+  ElMSCSampleKernel<true><<<OneWave(h, ElMSCSampleKernel<true>, n), kThreadsPerBlock, 0, side[0]>>>(h->view, *dev, w, seed);
+  G4H_CUDA(t.After(kSMscPos, side[0]));
+  if (!alone) {
+    G4H_CUDA(cudaEventRecord(slot.join[0], slot.aux[0]));
+    G4H_CUDA(cudaStreamWaitEvent(st, slot.join[0], 0));
+  }
   G4H_STAGE(kSFluct, ElFluctuationKernel<<<OneWave(h, ElFluctuationKernel, n), kThreadsPerBlock, 0, st>>>(h->view, *dev, w, seed));
   G4H_STAGE(kSDiscrete, ElDiscreteKernel<<<OneWave(h, ElDiscreteKernel, n), kThreadsPerBlock, 0, st>>>(h->view, *dev, w, seed));
 #undef G4H_STAGE
   // fork: the six samplers read disjoint queues and write disjoint tracks (+ atomic appends of secondaries)
-  G4H_CUDA(cudaEventRecord(slot.fork, st));
-  for (int k = 0; k < G4HB200::WorkSlot::kNumAux; ++k) G4H_CUDA(cudaStreamWaitEvent(slot.aux[k], slot.fork, 0));
+  if (!alone) {
+    G4H_CUDA(cudaEventRecord(slot.fork, st));
+    for (int k = 0; k < G4HB200::WorkSlot::kNumAux; ++k) G4H_CUDA(cudaStreamWaitEvent(slot.aux[k], slot.fork, 0));
+  }
 #define G4H_STAGE(stage, on, ...)   \
   G4H_CUDA(t.Before(stage, on));    \
   __VA_ARGS__;                      \
   G4H_CUDA(t.After(stage, on))
   G4H_STAGE(kSRB, st, ElSamplerKernel<kQRB><<<OneWave(h, ElSamplerKernel<kQRB>, n), kThreadsPerBlock, 0, st>>>(h->view, *dev, w, *sec, seed));
-  G4H_STAGE(kSSB, slot.aux[0], ElSamplerKernel<kQSB><<<OneWave(h, ElSamplerKernel<kQSB>, n), kThreadsPerBlock, 0, slot.aux[0]>>>(h->view, *dev, w, *sec, seed));
-  G4H_STAGE(kSBhabha, slot.aux[1], ElSamplerKernel<kQBhabha><<<OneWave(h, ElSamplerKernel<kQBhabha>, n), kThreadsPerBlock, 0, slot.aux[1]>>>(h->view, *dev, w, *sec, seed));
-  G4H_STAGE(kSMoller, slot.aux[2], ElSamplerKernel<kQMoller><<<OneWave(h, ElSamplerKernel<kQMoller>, n), kThreadsPerBlock, 0, slot.aux[2]>>>(h->view, *dev, w, *sec, seed));
-  G4H_STAGE(kSAnnih, slot.aux[3], ElSamplerKernel<kQAnnih><<<OneWave(h, ElSamplerKernel<kQAnnih>, n), kThreadsPerBlock, 0, slot.aux[3]>>>(h->view, *dev, w, *sec, seed));
-  G4H_STAGE(kSAtRest, slot.aux[4], ElSamplerKernel<kQAtRest><<<OneWave(h, ElSamplerKernel<kQAtRest>, n), kThreadsPerBlock, 0, slot.aux[4]>>>(h->view, *dev, w, *sec, seed));
-  for (int k = 0; k < G4HB200::WorkSlot::kNumAux; ++k) {
-    G4H_CUDA(cudaEventRecord(slot.join[k], slot.aux[k]));
-    G4H_CUDA(cudaStreamWaitEvent(st, slot.join[k], 0));
+  G4H_STAGE(kSSB, side[0], ElSamplerKernel<kQSB><<<OneWave(h, ElSamplerKernel<kQSB>, n), kThreadsPerBlock, 0, side[0]>>>(h->view, *dev, w, *sec, seed));
+  G4H_STAGE(kSBhabha, side[1], ElSamplerKernel<kQBhabha><<<OneWave(h, ElSamplerKernel<kQBhabha>, n), kThreadsPerBlock, 0, side[1]>>>(h->view, *dev, w, *sec, seed));
+  G4H_STAGE(kSMoller, side[2], ElSamplerKernel<kQMoller><<<OneWave(h, ElSamplerKernel<kQMoller>, n), kThreadsPerBlock, 0, side[2]>>>(h->view, *dev, w, *sec, seed));
+  G4H_STAGE(kSAnnih, side[3], ElSamplerKernel<kQAnnih><<<OneWave(h, ElSamplerKernel<kQAnnih>, n), kThreadsPerBlock, 0, side[3]>>>(h->view, *dev, w, *sec, seed));
+  G4H_STAGE(kSAtRest, side[4], ElSamplerKernel<kQAtRest><<<OneWave(h, ElSamplerKernel<kQAtRest>, n), kThreadsPerBlock, 0, side[4]>>>(h->view, *dev, w, *sec, seed));
+  if (!alone) {
+    for (int k = 0; k < G4HB200::WorkSlot::kNumAux; ++k) {
+      G4H_CUDA(cudaEventRecord(slot.join[k], slot.aux[k]));
+      G4H_CUDA(cudaStreamWaitEvent(st, slot.join[k], 0));
+    }
   }
 #undef G4H_STAGE
   if (t.tc != nullptr) {
@@ -481,20 +494,27 @@ int LaunchGammaPipeline(G4HB200* h, G4HB200GammaBatch* dev, G4HB200SecondaryQueu
   G4H_CUDA(t.Before(kSGammaHead));
   GammaHeadKernel<kMode><<<OneWave(h, GammaHeadKernel<kMode>, n), kThreadsPerBlock, 0, st>>>(h->view, *dev, w, seed);
   G4H_CUDA(t.After(kSGammaHead));
-  G4H_CUDA(cudaEventRecord(slot.fork, st));
-  for (int k = 0; k < 2; ++k) G4H_CUDA(cudaStreamWaitEvent(slot.aux[k], slot.fork, 0));
+  // the three samplers side by side; alone on the caller's stream when per-kernel timing is on
+  const bool alone = t.tc != nullptr;
+  cudaStream_t side[2] = {alone ? st : slot.aux[0], alone ? st : slot.aux[1]};
+  if (!alone) {
+    G4H_CUDA(cudaEventRecord(slot.fork, st));
+    for (int k = 0; k < 2; ++k) G4H_CUDA(cudaStreamWaitEvent(slot.aux[k], slot.fork, 0));
+  }
   G4H_CUDA(t.Before(kSGammaCompton, st));
   GammaInteractKernel<kGQCompton><<<OneWave(h, GammaInteractKernel<kGQCompton>, n), kThreadsPerBlock, 0, st>>>(h->view, *dev, w, *sec, seed);
   G4H_CUDA(t.After(kSGammaCompton, st));
-  G4H_CUDA(t.Before(kSGammaConversion, slot.aux[0]));
-  GammaInteractKernel<kGQConversion><<<OneWave(h, GammaInteractKernel<kGQConversion>, n), kThreadsPerBlock, 0, slot.aux[0]>>>(h->view, *dev, w, *sec, seed);
-  G4H_CUDA(t.After(kSGammaConversion, slot.aux[0]));
-  G4H_CUDA(t.Before(kSGammaPhotoelectric, slot.aux[1]));
-  GammaInteractKernel<kGQPhotoelectric><<<OneWave(h, GammaInteractKernel<kGQPhotoelectric>, n), kThreadsPerBlock, 0, slot.aux[1]>>>(h->view, *dev, w, *sec, seed);
-  G4H_CUDA(t.After(kSGammaPhotoelectric, slot.aux[1]));
-  for (int k = 0; k < 2; ++k) {
-    G4H_CUDA(cudaEventRecord(slot.join[k], slot.aux[k]));
-    G4H_CUDA(cudaStreamWaitEvent(st, slot.join[k], 0));
+  G4H_CUDA(t.Before(kSGammaConversion, side[0]));
+  GammaInteractKernel<kGQConversion><<<OneWave(h, GammaInteractKernel<kGQConversion>, n), kThreadsPerBlock, 0, side[0]>>>(h->view, *dev, w, *sec, seed);
+  G4H_CUDA(t.After(kSGammaConversion, side[0]));
+  G4H_CUDA(t.Before(kSGammaPhotoelectric, side[1]));
+  GammaInteractKernel<kGQPhotoelectric><<<OneWave(h, GammaInteractKernel<kGQPhotoelectric>, n), kThreadsPerBlock, 0, side[1]>>>(h->view, *dev, w, *sec, seed);
+  G4H_CUDA(t.After(kSGammaPhotoelectric, side[1]));
+  if (!alone) {
+    for (int k = 0; k < 2; ++k) {
+      G4H_CUDA(cudaEventRecord(slot.join[k], slot.aux[k]));
+      G4H_CUDA(cudaStreamWaitEvent(st, slot.join[k], 0));
+    }
   }
   if (t.tc != nullptr) {
     G4H_CUDA(cudaMemcpyAsync(t.tc->counts, w.count, kNumElQueues * sizeof(int32_t), cudaMemcpyDeviceToHost, st));

@@ -78,7 +78,7 @@ ElAlongStepKernel(const __grid_constant__ TablesView tv, const __grid_constant__
   cc.Init();
   for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < nRound; i += stride) {
     const int route = i < b.n ? StageAlongStep(tv, b, w.prestep, i) : -1;
-    // kQFluct, kQDiscrete, kQAtRest, kQMscEl, kQMscPos are queues 0..4
+    // kQMscEl, kQMscPos, kQFluct, kQDiscrete, kQAtRest are queues 0..4
     RouteToQueues<5>(cc, route, static_cast<int32_t>(i), w.queue, w.count);
   }
 }
@@ -116,7 +116,8 @@ ElMSCSampleKernel(const __grid_constant__ TablesView tv, const __grid_constant__
       i = queue[q];
       route = StageMSCSample<kPositron>(tv, b, w.prestep, i, seed, cbeta1);
     }
-    RouteToQueues<3>(cc, route, i, w.queue, w.count);
+    // kQFluct, kQDiscrete, kQAtRest are three consecutive queues
+    RouteToQueues<3>(cc, route < 0 ? -1 : route - kQFluct, i, w.queue + kQFluct, w.count + kQFluct);
   }
 }
 
@@ -127,7 +128,7 @@ ElFluctuationKernel(const __grid_constant__ TablesView tv, const __grid_constant
   const int cnt = w.count[kQFluct];
   const int nRound = static_cast<int>(RoundUpToCta(cnt));
   const int stride = gridDim.x * blockDim.x;
-  __shared__ CtaCounters<2> cc;
+  __shared__ CtaCounters<6> cc;
   __shared__ double window[G4H_WINDOW_FLUCT * kThreadsPerBlock];
   cc.Init();
   for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < nRound; q += stride) {
@@ -137,7 +138,8 @@ ElFluctuationKernel(const __grid_constant__ TablesView tv, const __grid_constant
       i = w.queue[kQFluct][q];
       route = StageFluctuation(tv, b, w.prestep, i, seed, window + threadIdx.x, kThreadsPerBlock, G4H_WINDOW_FLUCT);
     }
-    RouteToQueues<2>(cc, route < 0 ? -1 : route - kQDiscrete, i, w.queue + kQDiscrete, w.count + kQDiscrete);
+    // kQAtRest, kQMoller .. kQAnnih are six consecutive queues
+    RouteToQueues<6>(cc, route < 0 ? -1 : route - kQAtRest, i, w.queue + kQAtRest, w.count + kQAtRest);
   }
 }
 

@@ -5,6 +5,8 @@
 // catch transcription mistakes before GPU time is spent; the parity claims rest on the `-m gpu` tests,
 // which run the CUDA kernels through the C-ABI.  Nothing under g4hepem_b200/ loads this library.
 #include <cstdint>
+#include <cstdio>
+#include <cstdlib>
 #include <vector>
 
 #include "../../g4hepem_b200/csrc/g4h_batch_io.cuh"
@@ -143,6 +145,10 @@ int g4hsim_electron_perform_staged(const G4HB200Tables* t, G4HB200ElectronBatch*
     const int r = fused ? StageStepHead(tv, *b, prestep.data(), i, seed) : StageAlongStep(tv, *b, prestep.data(), i);
     if (r >= 0) queue[r].push_back(i);
   }
+  if (std::getenv("G4HSIM_ROUTES") != nullptr) {
+    std::fprintf(stderr, "after head: mscEl=%zu mscPos=%zu fluct=%zu discrete=%zu atRest=%zu\n", queue[kQMscEl].size(),
+                 queue[kQMscPos].size(), queue[kQFluct].size(), queue[kQDiscrete].size(), queue[kQAtRest].size());
+  }
   const double cbeta1 = MscCBeta1();
   for (int64_t i : queue[kQMscEl]) {
     const int r = StageMSCSample<false>(tv, *b, prestep.data(), i, seed, cbeta1);
@@ -152,9 +158,17 @@ int g4hsim_electron_perform_staged(const G4HB200Tables* t, G4HB200ElectronBatch*
     const int r = StageMSCSample<true>(tv, *b, prestep.data(), i, seed, cbeta1);
     if (r >= 0) queue[r].push_back(i);
   }
+  if (std::getenv("G4HSIM_ROUTES") != nullptr) {
+    std::fprintf(stderr, "after msc: fluct=%zu discrete=%zu atRest=%zu\n", queue[kQFluct].size(), queue[kQDiscrete].size(),
+                 queue[kQAtRest].size());
+  }
   for (int64_t i : queue[kQFluct]) {
     const int r = StageFluctuation(tv, *b, prestep.data(), i, seed);
     if (r >= 0) queue[r].push_back(i);
+  }
+  if (std::getenv("G4HSIM_ROUTES") != nullptr) {
+    std::fprintf(stderr, "routes: n=%ld mscEl=%zu mscPos=%zu fluct=%zu discrete=%zu atRest=%zu\n", static_cast<long>(b->n),
+                 queue[kQMscEl].size(), queue[kQMscPos].size(), queue[kQFluct].size(), queue[kQDiscrete].size(), queue[kQAtRest].size());
   }
   for (int64_t i : queue[kQDiscrete]) {
     const int r = StageDiscrete(tv, *b, i, seed);

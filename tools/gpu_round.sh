@@ -3,10 +3,10 @@
 mkdir -p gpurun_out
 python -m pytest tests -m gpu -q 2>&1 | tail -30 > gpurun_out/pytest_gpu.log
 python bench.py --steps 20 --warmup 3 > gpurun_out/bench.json 2> gpurun_out/bench.err
-ncu --metrics gpu__time_duration.sum --clock-control none -k regex:"^(El|Gamma)" -s 42 -c 78 --csv --log-file gpurun_out/launches.csv \
+ncu --metrics gpu__time_duration.sum --clock-control none -k regex:"^(El|Gamma)" -s 44 -c 88 --csv --log-file gpurun_out/launches.csv \
     python bench.py --steps 5 --warmup 3 --e2e-steps 2 --no-cpu-baseline > gpurun_out/bench_under_ncu.log 2>&1
 if [ "$1" == "full" ]; then
-ncu --set full --clock-control none --import-source on -k regex:"^(El|Gamma)" -c 16 -f -o gpurun_out/prof_pipeline \
+G4HB200_SPLIT_PARTS=1 ncu --set full --clock-control none --import-source on -k regex:"^(El|Gamma)" -c 16 -f -o gpurun_out/prof_pipeline \
     python tools/kernel_probe.py 1048576 1 > gpurun_out/prof_pipeline.log 2>&1
 fi
 tail -5 gpurun_out/pytest_gpu.log; cat gpurun_out/bench.json; tail -3 gpurun_out/bench.err

@@ -126,7 +126,7 @@ def test_electron_howfar_then_perform_multi_step(engine, reference, flat_tables)
 
     from g4hepem_b200 import engine as eng
 
-    n = 100000
+    n = 300000  # >= 256k: the Perform pipeline runs as two half-batch pipelines
     a = batches.make_electron_batch(n, flat_tables.num_matcut, seed=5)
     dev = eng.ElectronDeviceBatch(n)
     sec = eng.SecondaryDeviceQueue(2 * n)

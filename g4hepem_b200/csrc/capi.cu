@@ -127,6 +127,8 @@ struct G4HB200 {
   // device batches of at least this many tracks run as two half-batch pipelines side by side (G4HB200_SPLIT_MIN)
   int64_t splitThreshold = 1 << 18;
   int splitParts = 2;  // G4HB200_SPLIT_PARTS, at most kNumSlots
+  cudaStream_t loopStream = nullptr;  // gamma chain of the stepping loops (capi_shower.inl)
+  cudaEvent_t loopFork = nullptr, loopJoin = nullptr;
   cudaEvent_t splitFork = nullptr, splitJoin[4] = {};
   // per-kernel timing (g4hb200_set_kernel_timing): one event row per timed pipeline call
   bool timing = false;
@@ -748,6 +750,11 @@ int g4hb200_destroy(G4HB200* h) {
     for (auto& a : slot.aux) if (a != nullptr) cudaStreamDestroy(a);
     for (auto& e : slot.join) if (e != nullptr) cudaEventDestroy(e);
     if (slot.fork != nullptr) cudaEventDestroy(slot.fork);
+  }
+  if (h->loopStream != nullptr) {
+    cudaStreamDestroy(h->loopStream);
+    cudaEventDestroy(h->loopFork);
+    cudaEventDestroy(h->loopJoin);
   }
   if (h->splitFork != nullptr) {
     cudaEventDestroy(h->splitFork);

@@ -158,6 +158,17 @@ int RunStepLoop(G4HB200* h, const G4HB200SlabGeometry* geom, int64_t numPrimarie
   if ((rc = EnsureElectronWork(h->gmSlot, capacity)) != 0) return fail(rc);
   if (h->splitParts > 1 && (rc = EnsureElectronWork(h->gmSlot2, capacity / 2 + 2 * kThreadsPerBlock)) != 0) return fail(rc);
   cudaStream_t st = h->stream;
+  // the e-/e+ chain and the gamma chain of an iteration are independent until the host reads the counts: they run
+  // side by side (st / sg).  Most iterations of a shower are in its tail, where a chain is a dozen launches over a
+  // few thousand tracks and bound by launch latency.
+  if (h->loopStream == nullptr) {
+    if (cudaStreamCreateWithFlags(&h->loopStream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreateWithFlags(&h->loopFork, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&h->loopJoin, cudaEventDisableTiming) != cudaSuccess) {
+      return fail(Fail(G4HB200_ECUDA, "loop stream"));
+    }
+  }
+  cudaStream_t sg = h->loopStream;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   cudaEventCreate(&ev0);
   cudaEventCreate(&ev1);
@@ -188,6 +199,8 @@ int RunStepLoop(G4HB200* h, const G4HB200SlabGeometry* geom, int64_t numPrimarie
     if (nEl > stats->peak_electrons) stats->peak_electrons = nEl;
     if (nGm > stats->peak_gammas) stats->peak_gammas = nGm;
     cudaMemsetAsync(s.score.nextCount, 0, 2 * sizeof(int32_t), st);
+    cudaEventRecord(h->loopFork, st);
+    cudaStreamWaitEvent(sg, h->loopFork, 0);
     s.el[cur].n = nEl;
     s.gm[cur].n = nGm;
     if (nEl > 0) {
@@ -207,22 +220,6 @@ int RunStepLoop(G4HB200* h, const G4HB200SlabGeometry* geom, int64_t numPrimarie
           g, b, s.elGeo[cur], s.el[nxt], s.elGeo[nxt], s.score);
       ++h->launches;
     }
-    if (nGm > 0) {
-      G4HB200GammaBatch& b = s.gm[cur];
-      g4hb200_secondary_queue_reset(h, &s.secGm, st);
-      if (mixed.enabled) {
-        if ((status = g4hb200_gamma_step(h, &b, &s.secGm, seed, st)) != 0) break;
-      } else {
-        if ((status = g4hb200_gamma_howfar(h, &b, seed, st)) != 0) break;
-        ShowerGeomKernel<true><<<OneWave(h, ShowerGeomKernel<true>, nGm), kThreadsPerBlock, 0, st>>>(
-            g, nGm, b.dirx_diry, b.dirz_nia0, b.gstep_mfp0, b.meta, s.gmGeo[cur]);
-        ++h->launches;
-        if ((status = g4hb200_gamma_perform(h, &b, &s.secGm, seed, st)) != 0) break;
-      }
-      ShowerGammaPostKernel<<<OneWave(h, ShowerGammaPostKernel, nGm), kThreadsPerBlock, 0, st>>>(
-          g, b, s.gmGeo[cur], s.gm[nxt], s.gmGeo[nxt], s.score);
-      ++h->launches;
-    }
     if (nEl > 0) {
       ShowerSecondaryKernel<<<OneWave(h, ShowerSecondaryKernel, 2 * nEl), kThreadsPerBlock, 0, st>>>(
           g, seed, s.secEl, s.el[cur].meta, s.elGeo[cur], s.el[nxt], s.elGeo[nxt], s.gm[nxt], s.gmGeo[nxt], s.score);
@@ -232,13 +229,29 @@ int RunStepLoop(G4HB200* h, const G4HB200SlabGeometry* geom, int64_t numPrimarie
       s.pinned[3] = 0;
     }
     if (nGm > 0) {
-      ShowerSecondaryKernel<<<OneWave(h, ShowerSecondaryKernel, 2 * nGm), kThreadsPerBlock, 0, st>>>(
+      G4HB200GammaBatch& b = s.gm[cur];
+      g4hb200_secondary_queue_reset(h, &s.secGm, sg);
+      if (mixed.enabled) {
+        if ((status = g4hb200_gamma_step(h, &b, &s.secGm, seed, sg)) != 0) break;
+      } else {
+        if ((status = g4hb200_gamma_howfar(h, &b, seed, sg)) != 0) break;
+        ShowerGeomKernel<true><<<OneWave(h, ShowerGeomKernel<true>, nGm), kThreadsPerBlock, 0, sg>>>(
+            g, nGm, b.dirx_diry, b.dirz_nia0, b.gstep_mfp0, b.meta, s.gmGeo[cur]);
+        ++h->launches;
+        if ((status = g4hb200_gamma_perform(h, &b, &s.secGm, seed, sg)) != 0) break;
+      }
+      ShowerGammaPostKernel<<<OneWave(h, ShowerGammaPostKernel, nGm), kThreadsPerBlock, 0, sg>>>(
+          g, b, s.gmGeo[cur], s.gm[nxt], s.gmGeo[nxt], s.score);
+      ++h->launches;
+      ShowerSecondaryKernel<<<OneWave(h, ShowerSecondaryKernel, 2 * nGm), kThreadsPerBlock, 0, sg>>>(
           g, seed, s.secGm, s.gm[cur].meta, s.gmGeo[cur], s.el[nxt], s.elGeo[nxt], s.gm[nxt], s.gmGeo[nxt], s.score);
       ++h->launches;
-      cudaMemcpyAsync(s.pinned + 4, s.secGm.count, sizeof(int32_t), cudaMemcpyDeviceToHost, st);
+      cudaMemcpyAsync(s.pinned + 4, s.secGm.count, sizeof(int32_t), cudaMemcpyDeviceToHost, sg);
     } else {
       s.pinned[4] = 0;
     }
+    cudaEventRecord(h->loopJoin, sg);
+    cudaStreamWaitEvent(st, h->loopJoin, 0);
     cudaMemcpyAsync(s.pinned, s.score.nextCount, 3 * sizeof(int32_t), cudaMemcpyDeviceToHost, st);
     const cudaError_t err = cudaStreamSynchronize(st);
     if (err != cudaSuccess) {

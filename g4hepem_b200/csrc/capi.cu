@@ -384,9 +384,15 @@ int LaunchElectronHowFar(G4HB200* h, G4HB200ElectronBatch* dev, uint64_t seed, v
 int EnsureAuxStreams(G4HB200::WorkSlot& slot);
 
 // G4HepEmElectronManager::Perform as a pipeline (g4h_pipeline.cuh); kFused: HowFar first
+// geometry step inside the fused head (the stepping loop over the slab calorimeter, capi_shower.inl)
+struct SlabHead {
+  SlabGeom g;
+  TrackGeo geo;
+};
+
 template <bool kFused>
 int LaunchElectronPipeline(G4HB200* h, G4HB200ElectronBatch* dev, G4HB200SecondaryQueue* sec, uint64_t seed, void* stream,
-                           int slotIndex = 0) {
+                           int slotIndex = 0, const SlabHead* slab = nullptr) {
   int rc = CheckHandle(h);
   if (rc != 0) return rc;
   if (dev == nullptr || dev->n < 0) return Fail(G4HB200_EINVAL, "bad electron batch");
@@ -406,7 +412,10 @@ int LaunchElectronPipeline(G4HB200* h, G4HB200ElectronBatch* dev, G4HB200Seconda
   G4H_CUDA(t.After(stage))
   G4HB200::WorkSlot& slot = h->slots[slotIndex];
   if ((rc = EnsureAuxStreams(slot)) != 0) return rc;
-  if (kFused) {
+  if (kFused && slab != nullptr) {
+    G4H_STAGE(kSStepHead, ShowerElectronHeadKernel<<<OneWave(h, ShowerElectronHeadKernel, n), kThreadsPerBlock, 0, st>>>(
+                              h->view, *dev, w, seed, slab->g, slab->geo));
+  } else if (kFused) {
     G4H_STAGE(kSStepHead, ElStepHeadKernel<<<OneWave(h, ElStepHeadKernel, n), kThreadsPerBlock, 0, st>>>(h->view, *dev, w, seed));
   } else {
     G4H_STAGE(kSAlongStep, ElAlongStepKernel<<<OneWave(h, ElAlongStepKernel, n), kThreadsPerBlock, 0, st>>>(h->view, *dev, w));
@@ -544,11 +553,12 @@ G4HB200ElectronBatch ElectronBatchView(const G4HB200ElectronBatch& full, int64_t
 // with two halves in flight they run next to the other half's arithmetic-bound head / MSC / fluctuation kernels.
 // Tracks are independent and the uniform stream is keyed per track, so the result does not depend on the split.
 template <bool kFused>
-int LaunchElectronPipelineHalves(G4HB200* h, G4HB200ElectronBatch* dev, G4HB200SecondaryQueue* sec, uint64_t seed, void* stream) {
+int LaunchElectronPipelineHalves(G4HB200* h, G4HB200ElectronBatch* dev, G4HB200SecondaryQueue* sec, uint64_t seed, void* stream,
+                                 const SlabHead* slab = nullptr) {
   int rc = CheckHandle(h);
   if (rc != 0) return rc;
   if (dev == nullptr || sec == nullptr || dev->n < h->splitThreshold || h->timing || h->splitParts < 2) {
-    return LaunchElectronPipeline<kFused>(h, dev, sec, seed, stream);
+    return LaunchElectronPipeline<kFused>(h, dev, sec, seed, stream, 0, slab);
   }
   if (dev->n > 0x7fffffff) return Fail(G4HB200_EINVAL, "batch too large (track indices are 32 bit)");
   const int parts = h->splitParts;
@@ -575,7 +585,15 @@ int LaunchElectronPipelineHalves(G4HB200* h, G4HB200ElectronBatch* dev, G4HB200S
     G4HB200SecondaryQueue q = *sec;
     q.parent_base = sec->parent_base + static_cast<int32_t>(lo);
     cudaStream_t ps = p == 0 ? st : h->slots[p].stream;
-    if ((rc = LaunchElectronPipeline<kFused>(h, &part, &q, seed, ps, p)) != 0) return rc;
+    SlabHead partSlab;
+    if (slab != nullptr) {
+      partSlab = *slab;
+      partSlab.geo.posx_posy += 2 * lo;
+      partSlab.geo.posz_pad += 2 * lo;
+      partSlab.geo.vol += lo;
+      partSlab.geo.nextVol += lo;
+    }
+    if ((rc = LaunchElectronPipeline<kFused>(h, &part, &q, seed, ps, p, slab != nullptr ? &partSlab : nullptr)) != 0) return rc;
   }
   for (int p = 1; p < parts; ++p) {
     G4H_CUDA(cudaEventRecord(h->splitJoin[p], h->slots[p].stream));

@@ -210,11 +210,10 @@ int RunStepLoop(G4HB200* h, const G4HB200SlabGeometry* geom, int64_t numPrimarie
         // no geometry: the fused step (the proposed step is accepted)
         if ((status = g4hb200_electron_step(h, &b, &s.secEl, seed, st)) != 0) break;
       } else {
-        if ((status = g4hb200_electron_howfar(h, &b, seed, st)) != 0) break;
-        ShowerGeomKernel<false><<<OneWave(h, ShowerGeomKernel<false>, nEl), kThreadsPerBlock, 0, st>>>(
-            g, nEl, b.dirx_diry, b.dirz_safety, b.gstep_pstep, b.meta, s.elGeo[cur]);
-        ++h->launches;
-        if ((status = g4hb200_electron_perform(h, &b, &s.secEl, seed, st)) != 0) break;
+        // HowFar + geometry step + Perform: the head of the pipeline does the first two and the along-step part of
+        // the third in one pass (ShowerElectronHeadKernel), the queue kernels of Perform follow
+        const SlabHead slab{g, s.elGeo[cur]};
+        if ((status = LaunchElectronPipelineHalves<true>(h, &b, &s.secEl, seed, st, &slab)) != 0) break;
       }
       ShowerElectronPostKernel<<<OneWave(h, ShowerElectronPostKernel, nEl), kThreadsPerBlock, 0, st>>>(
           g, b, s.elGeo[cur], s.el[nxt], s.elGeo[nxt], s.score);

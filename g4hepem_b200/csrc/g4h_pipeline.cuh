@@ -92,7 +92,7 @@ ElStepHeadKernel(const __grid_constant__ TablesView tv, const __grid_constant__ 
   __shared__ CtaCounters<5> cc;
   cc.Init();
   for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < nRound; i += stride) {
-    const int route = i < b.n ? StageStepHead(tv, b, w.prestep, i, seed) : -1;
+    const int route = i < b.n ? StageStepHead(tv, b, w.prestep, i, seed, NoGeometryStep{}) : -1;
     RouteToQueues<5>(cc, route, static_cast<int32_t>(i), w.queue, w.count);
   }
 }

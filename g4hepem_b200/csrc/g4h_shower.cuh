@@ -23,6 +23,7 @@
 #define G4H_SHOWER_CUH
 
 #include "g4h_kernels.cuh"
+#include "g4h_pipeline.cuh"
 
 namespace g4h {
 
@@ -96,7 +97,54 @@ G4H_FN double SlabSafety(const SlabGeom& g, int vol, const double* pos) {
   return Max(0.0, s);
 }
 
+// the geometry step of one e-/e+ track between HowFar and Perform, on registers (for the fused head of the loop):
+// distance to the faces of the current slab along the direction, step = min(physics, geometry), post-step boundary
+// flag, move.  The same arithmetic as ShowerGeomKernel.
+struct SlabGeometryStep {
+  const SlabGeom& g;  // the kernel's __grid_constant__ parameter (indexed dynamically: a copy would live in local memory)
+  const TrackGeo& geo;
+  const double* dirx_diry;
+  G4H_MFN void operator()(int64_t i, ElectronState& s, double dirz) const {
+    const Pair dxy = LoadPair(dirx_diry, i);
+    const Pair pxy = LoadPair(geo.posx_posy, i);
+    const Pair pz  = LoadPair(geo.posz_pad, i);
+    const int vol  = geo.vol[i];
+    const double dir[3] = {dxy.a, dxy.b, dirz};
+    double pos[3] = {pxy.a, pxy.b, pz.a};
+    int nextVol;
+    const double dist = DistanceToBoundary(g, vol, pos, dir, nextVol);
+    double step = s.gStep;
+    const bool onBoundary = dist < step;
+    if (onBoundary) step = dist;
+    pos[0] += step * dir[0];
+    pos[1] += step * dir[1];
+    pos[2] += step * dir[2];
+    StorePair(geo.posx_posy, i, pos[0], pos[1]);
+    StorePair(geo.posz_pad, i, pos[2], 0.0);
+    geo.nextVol[i] = nextVol;
+    s.gStep      = step;
+    s.onBoundary = onBoundary;
+  }
+};
+
 #if defined(__CUDACC__)
+// ---- the head of an e-/e+ step of the loop: HowFar + geometry step + along-step part of Perform in one pass ---------
+// (g4h_stages.cuh: StageStepHead; replaces ElHowFarXSKernel + ElHowFarMSCKernel + ShowerGeomKernel + ElAlongStepKernel)
+__global__ void __launch_bounds__(kThreadsPerBlock, G4H_MINB_HEAD)
+ShowerElectronHeadKernel(const __grid_constant__ TablesView tv, const __grid_constant__ G4HB200ElectronBatch b,
+                         const __grid_constant__ ElectronWork w, uint64_t seed, const __grid_constant__ SlabGeom g,
+                         const __grid_constant__ TrackGeo geo) {
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  const int64_t nRound = RoundUpToCta(b.n);
+  __shared__ CtaCounters<5> cc;
+  cc.Init();
+  const SlabGeometryStep geometry{g, geo, b.dirx_diry};
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < nRound; i += stride) {
+    const int route = i < b.n ? StageStepHead(tv, b, w.prestep, i, seed, geometry) : -1;
+    RouteToQueues<5>(cc, route, static_cast<int32_t>(i), w.queue, w.count);
+  }
+}
+
 // ---- geometry step: between HowFar and Perform ------------------------------------------------------------------
 // kGamma: the batch is a gamma batch (groups gstep_mfp0 / dirz_nia0), else an e-/e+ batch (gstep_pstep / dirz_safety)
 template <bool kGamma>

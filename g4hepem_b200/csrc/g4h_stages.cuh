@@ -391,8 +391,15 @@ G4H_FN int ResampleNumIALeftWindow(double* nIA, const DrawWindow& dw) {
   return count;
 }
 
+// What happens between HowFar and Perform: nothing (the proposed step is accepted) ...
+struct NoGeometryStep {
+  G4H_MFN void operator()(int64_t, ElectronState&, double) const {}
+};
+// ... or a geometry step (g4h_shower.cuh: SlabGeometryStep) that shortens s.gStep and sets the post-step s.onBoundary.
 // returns the queue the track goes to next (kQFluct, kQDiscrete, kQAtRest, kQMscEl, kQMscPos) or -1
-G4H_FN int StageStepHead(const TablesView& tv, const G4HB200ElectronBatch& b, double* prestep, int64_t i, uint64_t seed) {
+template <class GeometryStep>
+G4H_FN int StageStepHead(const TablesView& tv, const G4HB200ElectronBatch& b, double* prestep, int64_t i, uint64_t seed,
+                         const GeometryStep& geometry) {
   const Meta m   = LoadMeta(b.meta, i);
   const Pair e   = LoadPair(b.ekin_logekin, i);
   const Pair n01 = LoadPair(b.nia01, i);
@@ -424,9 +431,12 @@ G4H_FN int StageStepHead(const TablesView& tv, const G4HB200ElectronBatch& b, do
   const double uA = nXS == 0 ? dw.u[0] : nXS == 1 ? dw.u[1] : nXS == 2 ? dw.u[2] : nXS == 3 ? dw.u[3] : dw.u[4];
   const double uB = nXS == 0 ? dw.u[1] : nXS == 1 ? dw.u[2] : nXS == 2 ? dw.u[3] : nXS == 3 ? dw.u[4] : dw.Sixth();
   const int nMSC = HowFarMSCCore(tv, s, hasGauss, gauss, uA, uB, dw.k0, dw.k1, static_cast<uint32_t>(m.draw + nXS));
-  // geometry accepts the step: fGStepLength and fOnBoundary stay; Perform, along-step part
+  // the geometry step (or none: fGStepLength and fOnBoundary stay); Perform, along-step part
+  geometry(i, s, dzs.a);
   const int route = AlongStepCore(tv, s);
-  f &= ~(G4HB200_F_MSC_FIRST_STEP | G4HB200_F_MSC_ACTIVE | G4HB200_F_MSC_DISPLACE | G4HB200_F_MSC_NO_SCATTER | G4HB200_F_GAUSS_CACHED);
+  f &= ~(G4HB200_F_ON_BOUNDARY | G4HB200_F_MSC_FIRST_STEP | G4HB200_F_MSC_ACTIVE | G4HB200_F_MSC_DISPLACE | G4HB200_F_MSC_NO_SCATTER |
+         G4HB200_F_GAUSS_CACHED);
+  if (s.onBoundary) f |= G4HB200_F_ON_BOUNDARY;
   if (s.mscFirstStep) f |= G4HB200_F_MSC_FIRST_STEP;
   if (s.mscActive) f |= G4HB200_F_MSC_ACTIVE;
   if (s.mscDisplace) f |= G4HB200_F_MSC_DISPLACE;

@@ -142,7 +142,7 @@ int g4hsim_electron_perform_staged(const G4HB200Tables* t, G4HB200ElectronBatch*
   std::vector<double> prestep(2 * static_cast<size_t>(b->n) + 2);
   std::vector<int64_t> queue[kNumElQueues];
   for (int64_t i = 0; i < b->n; ++i) {
-    const int r = fused ? StageStepHead(tv, *b, prestep.data(), i, seed) : StageAlongStep(tv, *b, prestep.data(), i);
+    const int r = fused ? StageStepHead(tv, *b, prestep.data(), i, seed, NoGeometryStep{}) : StageAlongStep(tv, *b, prestep.data(), i);
     if (r >= 0) queue[r].push_back(i);
   }
   if (std::getenv("G4HSIM_ROUTES") != nullptr) {

@@ -486,7 +486,7 @@ int EnsureAuxStreams(G4HB200::WorkSlot& slot) {
 // final state samplers side by side over their queues (g4h_pipeline.cuh); kMode 1: Perform, 2: fused step
 template <int kMode>
 int LaunchGammaPipeline(G4HB200* h, G4HB200GammaBatch* dev, G4HB200SecondaryQueue* sec, uint64_t seed, void* stream,
-                        bool secondSlot = false) {
+                        bool secondSlot = false, const SlabHead* slab = nullptr) {
   int rc = CheckHandle(h);
   if (rc != 0) return rc;
   if (dev == nullptr || dev->n < 0) return Fail(G4HB200_EINVAL, "bad gamma batch");
@@ -503,7 +503,11 @@ int LaunchGammaPipeline(G4HB200* h, G4HB200GammaBatch* dev, G4HB200SecondaryQueu
   StageTimer t{h, st};
   G4H_CUDA(t.Begin(n));
   G4H_CUDA(t.Before(kSGammaHead));
-  GammaHeadKernel<kMode><<<OneWave(h, GammaHeadKernel<kMode>, n), kThreadsPerBlock, 0, st>>>(h->view, *dev, w, seed);
+  if (kMode == 2 && slab != nullptr) {
+    ShowerGammaHeadKernel<<<OneWave(h, ShowerGammaHeadKernel, n), kThreadsPerBlock, 0, st>>>(h->view, *dev, w, seed, slab->g, slab->geo);
+  } else {
+    GammaHeadKernel<kMode><<<OneWave(h, GammaHeadKernel<kMode>, n), kThreadsPerBlock, 0, st>>>(h->view, *dev, w, seed);
+  }
   G4H_CUDA(t.After(kSGammaHead));
   // the three samplers side by side; alone on the caller's stream when per-kernel timing is on
   const bool alone = t.tc != nullptr;
@@ -615,11 +619,12 @@ G4HB200GammaBatch GammaBatchView(const G4HB200GammaBatch& full, int64_t lo, int6
 
 // the gamma pipeline of a large device batch as two half-batch pipelines side by side (see the e-/e+ one above)
 template <int kMode>
-int LaunchGammaPipelineHalves(G4HB200* h, G4HB200GammaBatch* dev, G4HB200SecondaryQueue* sec, uint64_t seed, void* stream) {
+int LaunchGammaPipelineHalves(G4HB200* h, G4HB200GammaBatch* dev, G4HB200SecondaryQueue* sec, uint64_t seed, void* stream,
+                              const SlabHead* slab = nullptr) {
   int rc = CheckHandle(h);
   if (rc != 0) return rc;
   if (dev == nullptr || sec == nullptr || dev->n < h->splitThreshold || h->timing || h->splitParts < 2) {
-    return LaunchGammaPipeline<kMode>(h, dev, sec, seed, stream);
+    return LaunchGammaPipeline<kMode>(h, dev, sec, seed, stream, false, slab);
   }
   if (dev->n > 0x7fffffff) return Fail(G4HB200_EINVAL, "batch too large (track indices are 32 bit)");
   G4HB200::WorkSlot& other = h->gmSlot2;
@@ -639,8 +644,16 @@ int LaunchGammaPipelineHalves(G4HB200* h, G4HB200GammaBatch* dev, G4HB200Seconda
   q1.parent_base = sec->parent_base + static_cast<int32_t>(n0);
   G4H_CUDA(cudaEventRecord(h->splitFork, st));
   G4H_CUDA(cudaStreamWaitEvent(other.stream, h->splitFork, 0));
-  if ((rc = LaunchGammaPipeline<kMode>(h, &first, sec, seed, st, false)) != 0) return rc;
-  if ((rc = LaunchGammaPipeline<kMode>(h, &second, &q1, seed, other.stream, true)) != 0) return rc;
+  SlabHead slab1;
+  if (slab != nullptr) {
+    slab1 = *slab;
+    slab1.geo.posx_posy += 2 * n0;
+    slab1.geo.posz_pad += 2 * n0;
+    slab1.geo.vol += n0;
+    slab1.geo.nextVol += n0;
+  }
+  if ((rc = LaunchGammaPipeline<kMode>(h, &first, sec, seed, st, false, slab)) != 0) return rc;
+  if ((rc = LaunchGammaPipeline<kMode>(h, &second, &q1, seed, other.stream, true, slab != nullptr ? &slab1 : nullptr)) != 0) return rc;
   G4H_CUDA(cudaEventRecord(h->splitJoin[0], other.stream));
   G4H_CUDA(cudaStreamWaitEvent(st, h->splitJoin[0], 0));
   return 0;

@@ -233,11 +233,9 @@ int RunStepLoop(G4HB200* h, const G4HB200SlabGeometry* geom, int64_t numPrimarie
       if (mixed.enabled) {
         if ((status = g4hb200_gamma_step(h, &b, &s.secGm, seed, sg)) != 0) break;
       } else {
-        if ((status = g4hb200_gamma_howfar(h, &b, seed, sg)) != 0) break;
-        ShowerGeomKernel<true><<<OneWave(h, ShowerGeomKernel<true>, nGm), kThreadsPerBlock, 0, sg>>>(
-            g, nGm, b.dirx_diry, b.dirz_nia0, b.gstep_mfp0, b.meta, s.gmGeo[cur]);
-        ++h->launches;
-        if ((status = g4hb200_gamma_perform(h, &b, &s.secGm, seed, sg)) != 0) break;
+        // HowFar + geometry step + SelectInteraction / Perform: one head kernel (ShowerGammaHeadKernel), then the samplers
+        const SlabHead slab{g, s.gmGeo[cur]};
+        if ((status = LaunchGammaPipelineHalves<2>(h, &b, &s.secGm, seed, sg, &slab)) != 0) break;
       }
       ShowerGammaPostKernel<<<OneWave(h, ShowerGammaPostKernel, nGm), kThreadsPerBlock, 0, sg>>>(
           g, b, s.gmGeo[cur], s.gm[nxt], s.gmGeo[nxt], s.score);

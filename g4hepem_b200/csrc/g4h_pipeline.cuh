@@ -201,7 +201,7 @@ GammaHeadKernel(const __grid_constant__ TablesView tv, const __grid_constant__ G
   __shared__ CtaCounters<3> cc;
   cc.Init();
   for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < nRound; i += stride) {
-    const int route = i < b.n ? StageGammaHead<kMode>(tv, b, i, seed) : -1;
+    const int route = i < b.n ? StageGammaHead<kMode>(tv, b, i, seed, NoGeometryStep{}) : -1;
     RouteToQueues<3>(cc, route, static_cast<int32_t>(i), w.queue, w.count);
   }
 }

@@ -127,7 +127,48 @@ struct SlabGeometryStep {
   }
 };
 
+// the same for a gamma track
+struct SlabGammaGeometryStep {
+  const SlabGeom& g;
+  const TrackGeo& geo;
+  G4H_MFN void operator()(int64_t i, GammaState& s) const {
+    const Pair pxy = LoadPair(geo.posx_posy, i);
+    const Pair pz  = LoadPair(geo.posz_pad, i);
+    const int vol  = geo.vol[i];
+    double pos[3] = {pxy.a, pxy.b, pz.a};
+    int nextVol;
+    const double dist = DistanceToBoundary(g, vol, pos, s.dir, nextVol);
+    double step = s.gStep;
+    const bool onBoundary = dist < step;
+    if (onBoundary) step = dist;
+    pos[0] += step * s.dir[0];
+    pos[1] += step * s.dir[1];
+    pos[2] += step * s.dir[2];
+    StorePair(geo.posx_posy, i, pos[0], pos[1]);
+    StorePair(geo.posz_pad, i, pos[2], 0.0);
+    geo.nextVol[i] = nextVol;
+    s.gStep      = step;
+    s.onBoundary = onBoundary;
+  }
+};
+
 #if defined(__CUDACC__)
+// ---- the head of a gamma step of the loop: HowFar + geometry step + SelectInteraction + head of Perform -------------
+__global__ void __launch_bounds__(kThreadsPerBlock, G4H_MINB_QUEUE)
+ShowerGammaHeadKernel(const __grid_constant__ TablesView tv, const __grid_constant__ G4HB200GammaBatch b,
+                      const __grid_constant__ ElectronWork w, uint64_t seed, const __grid_constant__ SlabGeom g,
+                      const __grid_constant__ TrackGeo geo) {
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  const int64_t nRound = RoundUpToCta(b.n);
+  __shared__ CtaCounters<3> cc;
+  cc.Init();
+  const SlabGammaGeometryStep geometry{g, geo};
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < nRound; i += stride) {
+    const int route = i < b.n ? StageGammaHead<2>(tv, b, i, seed, geometry) : -1;
+    RouteToQueues<3>(cc, route, static_cast<int32_t>(i), w.queue, w.count);
+  }
+}
+
 // ---- the head of an e-/e+ step of the loop: HowFar + geometry step + along-step part of Perform in one pass ---------
 // (g4h_stages.cuh: StageStepHead; replaces ElHowFarXSKernel + ElHowFarMSCKernel + ShowerGeomKernel + ElAlongStepKernel)
 __global__ void __launch_bounds__(kThreadsPerBlock, G4H_MINB_HEAD)

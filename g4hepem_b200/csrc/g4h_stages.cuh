@@ -394,6 +394,7 @@ G4H_FN int ResampleNumIALeftWindow(double* nIA, const DrawWindow& dw) {
 // What happens between HowFar and Perform: nothing (the proposed step is accepted) ...
 struct NoGeometryStep {
   G4H_MFN void operator()(int64_t, ElectronState&, double) const {}
+  G4H_MFN void operator()(int64_t, GammaState&) const {}
 };
 // ... or a geometry step (g4h_shower.cuh: SlabGeometryStep) that shortens s.gStep and sets the post-step s.onBoundary.
 // returns the queue the track goes to next (kQFluct, kQDiscrete, kQAtRest, kQMscEl, kQMscPos) or -1
@@ -465,14 +466,19 @@ G4H_FN int StageStepHead(const TablesView& tv, const G4HB200ElectronBatch& b, do
 //                        UpdateNumIALeft and the head of Perform (.icc:54-76): returns the process that interacts
 //                        (0 conversion, 1 Compton, 2 photoelectric) or -1
 //   StageGammaInteract   the final state sampler of that process + the tracking cut (.icc:77-94), over a queue
-template <int kMode>
-G4H_FN int StageGammaHead(const TablesView& tv, const G4HB200GammaBatch& b, int64_t i, uint64_t seed) {
+// geometry (kMode 2 only): what happens between HowFar and Perform, see NoGeometryStep
+template <int kMode, class GeometryStep>
+G4H_FN int StageGammaHead(const TablesView& tv, const G4HB200GammaBatch& b, int64_t i, uint64_t seed, const GeometryStep& geometry) {
   GammaState s;
   Rng rng;
   LoadGamma(b, i, seed, s, rng);
-  const int flags = b.meta[4 * i + 1];
+  int flags = b.meta[4 * i + 1];
   if (kMode == 1) LoadGammaHandOver(b, i, s);
-  if (kMode == 2) GammaHowFar(tv, s, rng);
+  if (kMode == 2) {
+    GammaHowFar(tv, s, rng);
+    geometry(i, s);
+    flags = s.onBoundary ? (flags | static_cast<int>(G4HB200_F_ON_BOUNDARY)) : (flags & ~static_cast<int>(G4HB200_F_ON_BOUNDARY));
+  }
   int route = -1;
   if (!s.onBoundary) {
     const double urnd = rng.Flat();

@@ -197,7 +197,7 @@ int g4hsim_gamma_staged(const G4HB200Tables* t, G4HB200GammaBatch* b, G4HB200Sec
   const TablesView tv = MakeView(*t);
   std::vector<int64_t> queue[3];
   for (int64_t i = 0; i < b->n; ++i) {
-    const int route = mode == 1 ? StageGammaHead<1>(tv, *b, i, seed) : StageGammaHead<2>(tv, *b, i, seed);
+    const int route = mode == 1 ? StageGammaHead<1>(tv, *b, i, seed, NoGeometryStep{}) : StageGammaHead<2>(tv, *b, i, seed, NoGeometryStep{});
     if (route >= 0) queue[route].push_back(i);
   }
   for (int k = 0; k < 3; ++k) {

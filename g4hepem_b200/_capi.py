@@ -154,6 +154,9 @@ class SlabGeometry(C.Structure):
         ("absorber_thickness", C.c_double * 4),
         ("absorber_couple", C.c_int32 * 4),
         ("half_yz", C.c_double),
+        ("woodcock_on", C.c_int32),
+        ("woodcock_couple", C.c_int32),
+        ("woodcock_ekin_min", C.c_double),
     ]
 
 
@@ -179,6 +182,7 @@ F_MSC_ACTIVE = 0x08
 F_MSC_DISPLACE = 0x10
 F_MSC_NO_SCATTER = 0x20
 F_GAUSS_CACHED = 0x40
+F_WDT_ON = 0x80
 
 SEC_ELECTRON, SEC_POSITRON, SEC_GAMMA = 0, 1, 2
 NUM_STAGES = 20

@@ -111,6 +111,10 @@ int RunStepLoop(G4HB200* h, const G4HB200SlabGeometry* geom, int64_t numPrimarie
   g.halfYZ = geom->half_yz;
   g.xFront = -0.5 * (g.numLayers * g.absFront[g.numAbsorbers]);
   g.inheritCouple = mixed.enabled ? 1 : 0;
+  g.wdtOn = (!mixed.enabled && geom->woodcock_on != 0) ? 1 : 0;
+  g.wdtCouple = geom->woodcock_couple;
+  g.wdtEkinMin = geom->woodcock_ekin_min;
+  if (g.wdtOn != 0 && (g.wdtCouple < 0 || g.wdtCouple >= h->view.numMatCut)) return Fail(G4HB200_EINVAL, "bad Woodcock couple");
   const int nbins = g.numLayers * g.numAbsorbers;
   std::memset(stats, 0, sizeof(*stats));
   for (int k = 0; k < nbins; ++k) edepOut[k] = 0.0;

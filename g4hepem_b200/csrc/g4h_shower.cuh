@@ -36,6 +36,8 @@ struct SlabGeom {
   int couple[kMaxAbsorbers];
   double halfYZ, xFront;               // xFront = -0.5 * numLayers * layer thickness
   int inheritCouple;                   // 1: no geometry (unbounded media): a secondary keeps its parent's couple
+  int wdtOn, wdtCouple;                // Woodcock tracking of gammas: on, the couple whose cross section is used
+  double wdtEkinMin;
 };
 
 // position / volume of the tracks of one store, next to its batch
@@ -127,27 +129,123 @@ struct SlabGeometryStep {
   }
 };
 
-// the same for a gamma track
+// distance from pos along dir to the surface of the whole calorimeter (the Woodcock tracking volume)
+G4H_FN double DistanceToCalorimeterOut(const SlabGeom& g, const double* pos, const double* dir) {
+  const double dx = DistanceAlong(pos[0], dir[0], g.xFront, -g.xFront);
+  const double dy = DistanceAlong(pos[1], dir[1], -g.halfYZ, g.halfYZ);
+  const double dz = DistanceAlong(pos[2], dir[2], -g.halfYZ, g.halfYZ);
+  return Min(dx, Min(dy, dz));
+}
+
+// the slab that holds the point x (inside the calorimeter): layer * numAbsorbers + absorber
+G4H_FN int LocateSlab(const SlabGeom& g, double x) {
+  const double layerT = g.absFront[g.numAbsorbers];
+  const double t = x - g.xFront;
+  int layer = static_cast<int>(t / layerT);
+  layer = layer < 0 ? 0 : (layer > g.numLayers - 1 ? g.numLayers - 1 : layer);
+  const double u = t - layer * layerT;
+  int iabs = g.numAbsorbers - 1;
+  for (int k = g.numAbsorbers - 1; k >= 1; --k) {
+    if (u < g.absFront[k]) iabs = k - 1;
+  }
+  return layer * g.numAbsorbers + iabs;
+}
+
+// The step limit of a gamma track of the loop and the geometry step behind it, on registers:
+//  - normally G4HepEmGammaManager::HowFar, then the distance to the faces of the current slab (ShowerGeomKernel);
+//  - under Woodcock tracking (g.wdtOn, energy above the limit, not within 1e-3 mm of the calorimeter surface)
+//    G4HepEmWoodcockHelper::KeepTracking (G4HepEmWoodcockHelper.cc:150-300) and the control flow around it in
+//    G4HepEmTrackingManager::TrackGamma (G4HepEmTrackingManager.cc:955-1053): exponential steps with the cross
+//    section of the Woodcock couple straight through the slab boundaries until a point is reached where the gamma
+//    really interacts -- for sure in the Woodcock material, with probability sigma(local) / sigma(Woodcock) elsewhere --
+//    or the surface of the calorimeter is 1e-3 mm away; then a zero step (interaction at that point) or a
+//    10 mm step that ends on the surface.  The number of interaction lengths left is reset in both cases.
+//    (A 10 mm step that does not end on a boundary -- `isWDTReachedBoundary && !geometryLimitedStep` -- cannot
+//    happen here: the surface of the calorimeter is a face of the slab the point is in, 1e-3 mm ahead.)
 struct SlabGammaGeometryStep {
   const SlabGeom& g;
   const TrackGeo& geo;
-  G4H_MFN void operator()(int64_t i, GammaState& s) const {
+  G4H_MFN void GammaHowFarAndStep(const TablesView& tv, int64_t i, GammaState& s, Rng& rng, int& flags) const {
     const Pair pxy = LoadPair(geo.posx_posy, i);
     const Pair pz  = LoadPair(geo.posz_pad, i);
-    const int vol  = geo.vol[i];
-    double pos[3] = {pxy.a, pxy.b, pz.a};
+    int vol        = geo.vol[i];
+    double pos[3]  = {pxy.a, pxy.b, pz.a};
+    double physicalStep;
+    bool wdt = false;
+    if (g.wdtOn != 0) {
+      // FindWDTVolume (.cc:105-147) unless already under Woodcock tracking, and the energy limit (TrackingManager.cc:966-972)
+      wdt = (static_cast<uint32_t>(flags) & G4HB200_F_WDT_ON) != 0u;
+      const double distOut = Max(DistanceToCalorimeterOut(g, pos, s.dir) - 1.0E-3, 0.0);
+      if (!wdt) wdt = !(s.ekin < g.wdtEkinMin) && !(distOut < 1.0E-6);
+      wdt = wdt && s.ekin > g.wdtEkinMin;
+      if (wdt) {
+        // KeepTracking
+        double distToBoundary = distOut;
+        const double lekin  = GetLogEKin(s);
+        const int wdtImat   = G4H_LD(tv.mcImat + g.wdtCouple);
+        double wdtPE = s.peMXsec;
+        const double wdtMXsec = GammaTotalMacXSec(tv, wdtImat, s.ekin, lekin, wdtPE);
+        const double kDblMax  = 1.7976931348623157e+308;
+        const double wdtMFP   = wdtMXsec > 0.0 ? 1.0 / wdtMXsec : kDblMax;
+        s.peMXsec = wdtPE;
+        double mxsec = 0.0;
+        int prevIMC  = -1;
+        bool doStop  = false;
+        bool reached = false;
+        double wdtStepLength = 0.0;
+        while (!doStop) {
+          const double pstep = wdtMFP < kDblMax ? -Log(rng.Flat()) * wdtMFP : kDblMax;
+          if (distToBoundary < pstep) {
+            wdtStepLength += distToBoundary;
+            reached = true;
+            doStop  = true;
+          } else {
+            wdtStepLength  += pstep;
+            distToBoundary -= pstep;
+            const int pvol = LocateSlab(g, pos[0] + wdtStepLength * s.dir[0]);
+            const int pimc = g.couple[pvol % g.numAbsorbers];
+            if (G4H_LD(tv.mcImat + pimc) != wdtImat) {
+              if (pimc != prevIMC) {
+                prevIMC = pimc;
+                mxsec   = GammaTotalMacXSec(tv, G4H_LD(tv.mcImat + pimc), s.ekin, lekin, s.peMXsec);
+              }
+              doStop = mxsec * wdtMFP > rng.Flat();
+              if (doStop) s.mfp0 = mxsec > 0.0 ? 1.0 / mxsec : kDblMax;
+            } else {
+              doStop    = true;
+              s.mfp0    = wdtMFP;
+              s.peMXsec = wdtPE;
+            }
+          }
+        }
+        pos[0] += wdtStepLength * s.dir[0];
+        pos[1] += wdtStepLength * s.dir[1];
+        pos[2] += wdtStepLength * s.dir[2];
+        vol     = LocateSlab(g, pos[0]);
+        s.imc   = g.couple[vol % g.numAbsorbers];
+        s.nIA0  = -1.0;
+        physicalStep = reached ? 10.0 : 0.0;
+        flags = reached ? (flags & ~static_cast<int>(G4HB200_F_WDT_ON)) : (flags | static_cast<int>(G4HB200_F_WDT_ON));
+      }
+    }
+    if (!wdt) {
+      flags &= ~static_cast<int>(G4HB200_F_WDT_ON);
+      GammaHowFar(tv, s, rng);
+      physicalStep = s.gStep;
+    }
     int nextVol;
     const double dist = DistanceToBoundary(g, vol, pos, s.dir, nextVol);
-    double step = s.gStep;
-    const bool onBoundary = dist < step;
-    if (onBoundary) step = dist;
+    const bool onBoundary = dist < physicalStep;
+    const double step = onBoundary ? dist : physicalStep;
     pos[0] += step * s.dir[0];
     pos[1] += step * s.dir[1];
     pos[2] += step * s.dir[2];
     StorePair(geo.posx_posy, i, pos[0], pos[1]);
     StorePair(geo.posz_pad, i, pos[2], 0.0);
+    geo.vol[i]     = vol;
     geo.nextVol[i] = nextVol;
-    s.gStep      = step;
+    // the track keeps the normal step length only: zero after Woodcock tracking (TrackingManager.cc:1038-1046)
+    s.gStep      = wdt ? 0.0 : step;
     s.onBoundary = onBoundary;
   }
 };

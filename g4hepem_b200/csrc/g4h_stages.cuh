@@ -394,7 +394,8 @@ G4H_FN int ResampleNumIALeftWindow(double* nIA, const DrawWindow& dw) {
 // What happens between HowFar and Perform: nothing (the proposed step is accepted) ...
 struct NoGeometryStep {
   G4H_MFN void operator()(int64_t, ElectronState&, double) const {}
-  G4H_MFN void operator()(int64_t, GammaState&) const {}
+  // gamma: the step limit and what follows it up to SelectInteraction; flags: the track's flag bits (in / out)
+  G4H_MFN void GammaHowFarAndStep(const TablesView& tv, int64_t, GammaState& s, Rng& rng, int&) const { GammaHowFar(tv, s, rng); }
 };
 // ... or a geometry step (g4h_shower.cuh: SlabGeometryStep) that shortens s.gStep and sets the post-step s.onBoundary.
 // returns the queue the track goes to next (kQFluct, kQDiscrete, kQAtRest, kQMscEl, kQMscPos) or -1
@@ -475,8 +476,7 @@ G4H_FN int StageGammaHead(const TablesView& tv, const G4HB200GammaBatch& b, int6
   int flags = b.meta[4 * i + 1];
   if (kMode == 1) LoadGammaHandOver(b, i, s);
   if (kMode == 2) {
-    GammaHowFar(tv, s, rng);
-    geometry(i, s);
+    geometry.GammaHowFarAndStep(tv, i, s, rng, flags);
     flags = s.onBoundary ? (flags | static_cast<int>(G4HB200_F_ON_BOUNDARY)) : (flags & ~static_cast<int>(G4HB200_F_ON_BOUNDARY));
   }
   int route = -1;

@@ -18,6 +18,10 @@ class SlabCalorimeter:
     absorber_thickness: tuple = (2.3, 5.7)   # mm: G4_Pb, G4_lAr
     absorber_couple: tuple = (1, 2)          # material-cuts couple of each absorber in the table set
     half_yz: float = 200.0                   # mm
+    # Woodcock tracking of gammas in the calorimeter (PhysListHepEmTracking.cc:42); couple = the densest absorber's
+    woodcock: bool = False
+    woodcock_couple: int = 1
+    woodcock_ekin_min: float = 0.2           # MeV, G4HepEmConfig::fWDTEnergyLimit
 
     def as_struct(self):
         g = _capi.SlabGeometry()
@@ -27,6 +31,9 @@ class SlabCalorimeter:
             g.absorber_thickness[k] = t
             g.absorber_couple[k] = c
         g.half_yz = self.half_yz
+        g.woodcock_on = 1 if self.woodcock else 0
+        g.woodcock_couple = self.woodcock_couple
+        g.woodcock_ekin_min = self.woodcock_ekin_min
         return g
 
     @property

@@ -140,6 +140,7 @@ typedef struct G4HB200Tables {
 #define G4HB200_F_MSC_DISPLACE 0x10u    /* fIsDisplace */
 #define G4HB200_F_MSC_NO_SCATTER 0x20u  /* fIsNoScatteringInMSC */
 #define G4HB200_F_GAUSS_CACHED 0x40u    /* G4HepEmRandomEngine::fIsGauss */
+#define G4HB200_F_WDT_ON 0x80u          /* gamma, stepping loop: under Woodcock tracking (isWDTOn of TrackGamma) */
 
 /* e-/e+ state: G4HepEmElectronTrack (G4HepEmRun/include/G4HepEmElectronTrack.hh:20-93) */
 typedef struct G4HB200ElectronBatch {
@@ -302,6 +303,14 @@ typedef struct G4HB200SlabGeometry {
   double absorber_thickness[4]; /* mm: 2.3 (Pb), 5.7 (lAr) */
   int32_t absorber_couple[4];   /* material-cuts couple index of each absorber */
   double half_yz;               /* half of fCalorSizeYZ (200 mm) */
+  /* Woodcock tracking of gammas with the calorimeter as the tracking region (G4HepEmWoodcockHelper,
+   * G4HepEm/G4HepEm/src/G4HepEmWoodcockHelper.cc:105-300; TestEm3 turns it on for its calorimeter region,
+   * apps/examples/TestEm3/src/PhysListHepEmTracking.cc:42): a gamma above woodcock_ekin_min steps with the
+   * cross section of woodcock_couple (the couple of the densest absorber) across the slab boundaries and
+   * interacts where it stops with probability sigma(local material) / sigma(woodcock material). */
+  int32_t woodcock_on;          /* 0: every gamma step ends on the slab boundaries (no Woodcock tracking) */
+  int32_t woodcock_couple;      /* G4HepEmWoodcockHelper::fWDTHepEmIMC */
+  double woodcock_ekin_min;     /* MeV; G4HepEmConfig::fWDTEnergyLimit (0.2) */
 } G4HB200SlabGeometry;
 
 typedef struct G4HB200ShowerStats {

@@ -40,6 +40,24 @@ def child_stream(seed, parent_id, parent_draw, slot):
     return a.astype(np.uint32).view(np.int32), (b & np.uint32(0x3FFFFFFE)).astype(np.int32)
 
 
+def uniform_at(seed, ids, draw):
+    """draw `draw[k]` of the counter based stream of track ids[k] (g4h_rng.cuh / oracle/g4h_rng_host.h)."""
+    n = len(ids)
+    c = np.zeros((n, 4), dtype=np.uint32)
+    c[:, 0] = (draw.astype(np.int64) >> 1).astype(np.uint32)
+    c[:, 2] = ids.astype(np.uint32)
+    r = philox4x32_10(c, np.array([seed & 0xFFFFFFFF, (seed >> 32) & 0xFFFFFFFF], dtype=np.uint64)).astype(np.uint64)
+    odd = (draw.astype(np.int64) & 1) == 1
+    lo = np.where(odd, r[:, 2], r[:, 0])
+    hi = np.where(odd, r[:, 3], r[:, 1])
+    bits = ((hi << np.uint64(32)) | lo) >> np.uint64(12)
+    d = (bits | np.uint64(0x3FF0000000000000)).view(np.float64)
+    return d - 0.99999999999999988897769753748
+
+
+DBL_MAX = np.finfo(np.float64).max
+
+
 class Slab:
     def __init__(self, calo):
         self.nl = calo.num_layers
@@ -77,6 +95,24 @@ class Slab:
         d = np.where(m, dz, d)
         nv = np.where(m, -1, nv)
         return d, nv.astype(np.int32)
+
+    def distance_out(self, pos, dirs):
+        """along dirs to the surface of the whole calorimeter (DistanceToCalorimeterOut)"""
+        dx = self.along(pos[:, 0], dirs[:, 0], self.xfront, -self.xfront)
+        dy = self.along(pos[:, 1], dirs[:, 1], -self.half, self.half)
+        dz = self.along(pos[:, 2], dirs[:, 2], -self.half, self.half)
+        return np.minimum(dx, np.minimum(dy, dz))
+
+    def locate(self, x):
+        """LocateSlab of g4h_shower.cuh"""
+        layer_t = self.front[self.na]
+        t = x - self.xfront
+        layer = np.clip((t / layer_t).astype(np.int64), 0, self.nl - 1)
+        u = t - layer * layer_t
+        iabs = np.full(len(x), self.na - 1, dtype=np.int64)
+        for k in range(self.na - 1, 0, -1):
+            iabs = np.where(u < self.front[k], k - 1, iabs)
+        return (layer * self.na + iabs).astype(np.int32)
 
     def safety(self, vol, pos):
         xlo, xhi = self.bounds(vol)
@@ -122,8 +158,115 @@ def _concat(parts, cls):
     return o
 
 
-def run(reference, calo, num_primaries, primary_ekin, seed, kind=_capi.SEC_ELECTRON, first_track_id=0, max_steps=0, threads=4):
-    """Returns (edep[num_layers, num_absorbers], stats) like g4hepem_b200.shower.run."""
+def _total_mxsec(reference, seed, imc, ekin, lekin, pe_prev):
+    """G4HepEmGammaManager::GetTotalMacXSec for (couple, energy): (total macroscopic cross section, fPEmxSec after the
+    call -- the previous value where the function does not set it), both from the reference."""
+    mx, _ = reference.gamma_lookups(imc.astype(np.int32), ekin, lekin, np.zeros(len(imc)))
+    scratch = _new_gammas(len(imc))
+    scratch.ekin_logekin[:, 0] = ekin
+    scratch.ekin_logekin[:, 1] = lekin
+    scratch.dirz_nia0[:, 1] = 1.0  # no resampling, no draw
+    scratch.meta[:, 0] = imc
+    scratch.edep_pemxsec[:, 1] = pe_prev
+    reference.gamma_howfar(scratch, seed, 1)
+    return mx, scratch.edep_pemxsec[:, 1].copy()
+
+
+def _woodcock(reference, slab, calo, couple_material, gm, gm_pos, dirs, seed):
+    """G4HepEmWoodcockHelper::KeepTracking (G4HepEmWoodcockHelper.cc:150-300) with the decisions around it in
+    G4HepEmTrackingManager::TrackGamma (G4HepEmTrackingManager.cc:955-1032), for the gammas it applies to; the same
+    operations in the same order as SlabGammaGeometryStep of g4h_shower.cuh.
+    Returns (wdt mask, physical step, positions, volumes of the wdt tracks after the Woodcock part)."""
+    n = gm.n
+    ekin = gm.ekin_logekin[:, 0]
+    lim = calo.woodcock_ekin_min
+    dout = np.maximum(slab.distance_out(gm_pos, dirs) - 1.0e-3, 0.0)
+    on = (gm.meta[:, 1] & _capi.F_WDT_ON) != 0
+    on = np.where(on, True, ~(ekin < lim) & ~(dout < 1.0e-6))
+    on = on & (ekin > lim)
+    idx = np.flatnonzero(on)
+    phys = np.zeros(n)
+    pos = gm_pos.copy()
+    vol = np.zeros(n, dtype=np.int32)
+    gm.meta[:, 1] = np.where(on, gm.meta[:, 1], gm.meta[:, 1] & ~_capi.F_WDT_ON)
+    if len(idx) == 0:
+        return on, phys, pos, vol
+    m = len(idx)
+    ek = ekin[idx]
+    lek = gm.ekin_logekin[idx, 1]
+    lek = np.where(lek > 99.0, reference.vdt_log_exp(ek)[0], lek)
+    gm.ekin_logekin[idx, 1] = lek
+    ids = gm.meta[idx, 2]
+    draw = gm.meta[idx, 3].astype(np.int64)
+    wimc = np.full(m, calo.woodcock_couple, dtype=np.int32)
+    wmat = couple_material[calo.woodcock_couple]
+    wmx, wpe = _total_mxsec(reference, seed, wimc, ek, lek, gm.edep_pemxsec[idx, 1])
+    with np.errstate(divide="ignore"):
+        wmfp = np.where(wmx > 0.0, 1.0 / wmx, DBL_MAX)
+    pe = wpe.copy()
+    dist = dout[idx].copy()
+    steplen = np.zeros(m)
+    reached = np.zeros(m, dtype=bool)
+    stop = np.zeros(m, dtype=bool)
+    mx = np.zeros(m)
+    prev = np.full(m, -1, dtype=np.int32)
+    mfp0 = np.full(m, -1.0)
+    d0 = dirs[idx, 0]
+    x0 = gm_pos[idx, 0]
+    while not stop.all():
+        a = np.flatnonzero(~stop)
+        need = wmfp[a] < DBL_MAX
+        u = np.ones(len(a))
+        if need.any():
+            u[need] = uniform_at(seed, ids[a][need], draw[a][need])
+            draw[a[need]] += 1
+        pstep = np.where(need, -reference.vdt_log_exp(u)[0] * wmfp[a], DBL_MAX)
+        hit = dist[a] < pstep
+        steplen[a] += np.where(hit, dist[a], pstep)
+        reached[a[hit]] = True
+        stop[a[hit]] = True
+        b = a[~hit]
+        if len(b) == 0:
+            continue
+        dist[b] -= pstep[~hit]
+        pvol = slab.locate(x0[b] + steplen[b] * d0[b])
+        pimc = slab.couple[pvol % slab.na]
+        same = couple_material[pimc] == wmat
+        bs = b[same]
+        stop[bs] = True
+        mfp0[bs] = wmfp[bs]
+        pe[bs] = wpe[bs]
+        bd = b[~same]
+        if len(bd) > 0:
+            pimc_d = pimc[~same]
+            changed = pimc_d != prev[bd]
+            if changed.any():
+                c = bd[changed]
+                prev[c] = pimc_d[changed]
+                mx[c], pe[c] = _total_mxsec(reference, seed, pimc_d[changed], ek[c], lek[c], pe[c])
+            u2 = uniform_at(seed, ids[bd], draw[bd])
+            draw[bd] += 1
+            st = mx[bd] * wmfp[bd] > u2
+            s_idx = bd[st]
+            stop[s_idx] = True
+            with np.errstate(divide="ignore"):
+                mfp0[s_idx] = np.where(mx[s_idx] > 0.0, 1.0 / mx[s_idx], DBL_MAX)
+    pos[idx] = gm_pos[idx] + steplen[:, None] * dirs[idx]
+    vol[idx] = slab.locate(pos[idx, 0])
+    gm.meta[idx, 0] = slab.couple[vol[idx] % slab.na]
+    gm.meta[idx, 3] = draw.astype(np.int32)
+    gm.dirz_nia0[idx, 1] = -1.0
+    gm.gstep_mfp0[idx, 1] = mfp0
+    gm.edep_pemxsec[idx, 1] = pe
+    phys[idx] = np.where(reached, 10.0, 0.0)
+    gm.meta[idx, 1] = np.where(reached, gm.meta[idx, 1] & ~_capi.F_WDT_ON, gm.meta[idx, 1] | _capi.F_WDT_ON)
+    return on, phys, pos, vol
+
+
+def run(reference, calo, num_primaries, primary_ekin, seed, kind=_capi.SEC_ELECTRON, first_track_id=0, max_steps=0, threads=4,
+        couple_material=None):
+    """Returns (edep[num_layers, num_absorbers], stats) like g4hepem_b200.shower.run.
+    couple_material: material index of every couple (needed with calo.woodcock)."""
     slab = Slab(calo)
     hist = np.zeros(slab.nl * slab.na)
     stats = dict(num_steps=0, electron_track_steps=0, gamma_track_steps=0, secondaries=0, peak_electrons=0, peak_gammas=0,
@@ -231,13 +374,26 @@ def run(reference, calo, num_primaries, primary_ekin, seed, kind=_capi.SEC_ELECT
             next_gm += [(cg, cgpos, cgvol)]
         # ---- gamma ------------------------------------------------------------------------------------------------------
         if gm.n > 0:
-            reference.gamma_howfar(gm, seed, threads)
             dirs = np.stack([gm.dirx_diry[:, 0], gm.dirx_diry[:, 1], gm.dirz_nia0[:, 0]], axis=1)
+            if getattr(calo, "woodcock", False):
+                wdt, phys, gm_pos, wvol = _woodcock(reference, slab, calo, np.asarray(couple_material), gm, gm_pos, dirs, seed)
+                gm_vol = np.where(wdt, wvol, gm_vol).astype(np.int32)
+                normal = np.flatnonzero(~wdt)
+                if len(normal) > 0:
+                    sub = _take(gm, normal, batches.GammaHostBatch)
+                    reference.gamma_howfar(sub, seed, threads)
+                    for g_ in sub.groups() + ("meta", "winner"):
+                        getattr(gm, g_)[normal] = getattr(sub, g_)
+                    phys[normal] = sub.gstep_mfp0[:, 0]
+            else:
+                wdt = np.zeros(gm.n, dtype=bool)
+                reference.gamma_howfar(gm, seed, threads)
+                phys = gm.gstep_mfp0[:, 0].copy()
             dist, nv = slab.distance(gm_vol, gm_pos, dirs)
-            onb = dist < gm.gstep_mfp0[:, 0]
-            step = np.where(onb, dist, gm.gstep_mfp0[:, 0])
+            onb = dist < phys
+            step = np.where(onb, dist, phys)
             gm_pos = gm_pos + step[:, None] * dirs
-            gm.gstep_mfp0[:, 0] = step
+            gm.gstep_mfp0[:, 0] = np.where(wdt, 0.0, step)
             gm.meta[:, 1] = np.where(onb, gm.meta[:, 1] | _capi.F_ON_BOUNDARY, gm.meta[:, 1] & ~_capi.F_ON_BOUNDARY)
             sec = batches.SecondaryHostQueue(2 * gm.n)
             reference.gamma_perform(gm, sec, seed, threads)

@@ -83,3 +83,34 @@ def test_mixed_population_steps(engine):
     assert abs(e1 - e2) <= 1e-9 * abs(e1)
     assert s1["electron_track_steps"] > 40000 and s1["gamma_track_steps"] > 20000
     assert s1["secondaries"] > 10000 and e1 > 0.0
+
+
+def test_oracle_loop_with_woodcock_tracking(reference, flat_tables):
+    """Woodcock tracking of the gammas (G4HepEmWoodcockHelper): the energy bookkeeping holds, the gammas take far
+    fewer steps (they no longer stop on every slab boundary) and the shower deposits its energy in the same place
+    within the statistics of a few showers."""
+    plain = shower.SlabCalorimeter()
+    wdt = shower.SlabCalorimeter(woodcock=True)
+    mat = flat_tables.couple_material()
+    h0, s0 = shower_oracle.run(reference, plain, 6, 300.0, SEED)
+    h1, s1 = shower_oracle.run(reference, wdt, 6, 300.0, SEED, couple_material=mat)
+    total = h1.sum() + s1["leak_electron"] + s1["leak_gamma"]
+    # kinetic energy in = deposits + leakage, up to 2 m_e c^2 for every e+ that leaves the calorimeter
+    missing = (6 * 300.0 - total) / (2 * 0.51099891)
+    assert missing > -1e-6 and abs(missing - round(missing)) < 1e-5 and round(missing) <= 3, missing
+    assert s1["gamma_track_steps"] < 0.6 * s0["gamma_track_steps"]
+    assert abs(h1[:, 0].sum() / h1.sum() - h0[:, 0].sum() / h0.sum()) < 0.08
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("kind,nprim,ekin", [(_capi.SEC_ELECTRON, 10, 400.0), (_capi.SEC_GAMMA, 12, 250.0)])
+def test_device_shower_with_woodcock_tracking_matches_cpu_loop(engine, reference, flat_tables, kind, nprim, ekin):
+    calo = shower.SlabCalorimeter(woodcock=True)
+    want, wst = shower_oracle.run(reference, calo, nprim, ekin, SEED, kind=kind, first_track_id=300,
+                                  couple_material=flat_tables.couple_material())
+    got = shower.run(engine, calo, nprim, ekin, SEED, kind=kind, first_track_id=300, capacity=1 << 16)
+    for k in ("num_steps", "electron_track_steps", "gamma_track_steps", "secondaries", "peak_electrons", "peak_gammas"):
+        assert got.stats[k] == wst[k], (k, got.stats[k], wst[k])
+    np.testing.assert_allclose(got.edep, want, rtol=1e-9, atol=1e-9)
+    assert abs(got.stats["leak_electron"] - wst["leak_electron"]) <= 1e-9 * max(1.0, wst["leak_electron"])
+    assert abs(got.stats["leak_gamma"] - wst["leak_gamma"]) <= 1e-9 * max(1.0, wst["leak_gamma"])

@@ -37,6 +37,7 @@ def main():
     ap.add_argument("--steps", type=int, default=4, help="config 3: consecutive steps")
     ap.add_argument("--capacity", type=int, default=0)
     ap.add_argument("--seed", type=int, default=2026)
+    ap.add_argument("--woodcock", action="store_true", help="config 4: Woodcock tracking of the gammas (TestEm3's default)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -57,7 +58,7 @@ def main():
         torch.cuda.synchronize()
 
     if args.config == 4:
-        calo = shower.SlabCalorimeter()
+        calo = shower.SlabCalorimeter(woodcock=args.woodcock)
         cap = args.capacity or max(1 << 18, args.primaries * 1536)
         shower.run(e, calo, min(8, args.primaries), min(args.ekin, 1000.0), args.seed, capacity=1 << 18)  # warm-up
         barrier()
@@ -77,7 +78,8 @@ def main():
             steps = cnt[0] + cnt[1]
             total_e = world * args.primaries * args.ekin
             line = {"config": f"BASELINE configs[4]: TestEm3 ATLASbar (50 x (2.3 mm Pb + 5.7 mm lAr)) {args.ekin / 1000:g} GeV e- showers, "
-                              f"{args.primaries} primaries per GPU, stepped until no track is left",
+                              f"{args.primaries} primaries per GPU, stepped until no track is left"
+                              + (", Woodcock tracking of gammas" if args.woodcock else ""),
                     "metric": "e-/e+/gamma track-steps/s", "value": steps / (ms * 1e-3), "unit": "track-steps/s", "n_gpus": world,
                     "scaling": "weak", "ms": ms, "primaries_total": world * args.primaries,
                     "primaries_per_s": world * args.primaries / (ms * 1e-3),

@@ -1,0 +1,21 @@
+#!/usr/bin/env python
+"""Small runs of every pipeline (fused step, HowFar + Perform, gamma step, showers with and without Woodcock tracking)
+for `compute-sanitizer --tool memcheck|racecheck python tools/sanitizer_probe.py` (r01c on the B200: 0 errors, 0 hazards)."""
+import os, sys
+sys.path.insert(0, os.getcwd())
+import numpy as np, torch
+from g4hepem_b200 import batches, engine as eng, tables, shower, _capi
+ft = tables.load_state_json("tests/golden/hepem_state.json")
+e = eng.Engine(ft, 0)
+n = 20000
+host = batches.make_electron_batch(n, ft.num_matcut, seed=3)
+dev = eng.ElectronDeviceBatch(n); sec = eng.SecondaryDeviceQueue(2 * n)
+dev.upload(host); eng.ElectronManager.Step(e, dev, sec, 2026); torch.cuda.synchronize()
+dev.upload(host); sec.reset(); eng.ElectronManager.HowFar(e, dev, 2026); eng.ElectronManager.Perform(e, dev, sec, 2026); torch.cuda.synchronize()
+g = batches.make_gamma_batch(n, ft.num_matcut, seed=4)
+gd = eng.GammaDeviceBatch(n); gs = eng.SecondaryDeviceQueue(2 * n)
+gd.upload(g); eng.GammaManager.Step(e, gd, gs, 2026); torch.cuda.synchronize()
+for w in (False, True):
+    r = shower.run(e, shower.SlabCalorimeter(woodcock=w), 4, 200.0, 2026, capacity=1 << 15)
+    print("shower", w, r.stats["num_steps"], float(r.edep.sum()))
+print("done")

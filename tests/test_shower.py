@@ -114,3 +114,20 @@ def test_device_shower_with_woodcock_tracking_matches_cpu_loop(engine, reference
     np.testing.assert_allclose(got.edep, want, rtol=1e-9, atol=1e-9)
     assert abs(got.stats["leak_electron"] - wst["leak_electron"]) <= 1e-9 * max(1.0, wst["leak_electron"])
     assert abs(got.stats["leak_gamma"] - wst["leak_gamma"]) <= 1e-9 * max(1.0, wst["leak_gamma"])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("woodcock", [False, True])
+def test_device_showers_at_scale_keep_the_energy_balance(engine, woodcock):
+    """512 x 1 GeV showers (populations of ~1e5 tracks: the half-batch pipelines, the two-stream loop): kinetic energy
+    in = deposits + leakage, up to 2 m_e c^2 per e+ that leaves the calorimeter."""
+    calo = shower.SlabCalorimeter(woodcock=woodcock)
+    nprim, ekin = 512, 1000.0
+    res = shower.run(engine, calo, nprim, ekin, SEED, capacity=1 << 21)
+    total = res.edep.sum() + res.stats["leak_electron"] + res.stats["leak_gamma"]
+    missing = (nprim * ekin - total) / (2 * 0.51099891)
+    assert missing > -1e-3 and abs(missing - round(missing)) < 1e-3 and round(missing) < 200, missing
+    assert res.stats["peak_electrons"] > 20000
+    # lead takes ~78 % of the deposit, liquid argon ~21 % (sampling fraction of the ATLASbar stack)
+    frac = res.edep[:, 0].sum() / res.edep.sum()
+    assert 0.7 < frac < 0.85, frac

@@ -137,6 +137,11 @@ G4H_FN double DistanceToCalorimeterOut(const SlabGeom& g, const double* pos, con
   return Min(dx, Min(dy, dz));
 }
 
+#ifndef G4H_WDT_MAX_VIRTUAL_STEPS
+#define G4H_WDT_MAX_VIRTUAL_STEPS 4
+#endif
+constexpr int kWdtMaxVirtualSteps = G4H_WDT_MAX_VIRTUAL_STEPS;
+
 // the slab that holds the point x (inside the calorimeter): layer * numAbsorbers + absorber
 G4H_FN int LocateSlab(const SlabGeom& g, double x) {
   const double layerT = g.absFront[g.numAbsorbers];
@@ -165,7 +170,7 @@ G4H_FN int LocateSlab(const SlabGeom& g, double x) {
 struct SlabGammaGeometryStep {
   const SlabGeom& g;
   const TrackGeo& geo;
-  G4H_MFN void GammaHowFarAndStep(const TablesView& tv, int64_t i, GammaState& s, Rng& rng, int& flags) const {
+  G4H_MFN bool GammaHowFarAndStep(const TablesView& tv, int64_t i, GammaState& s, Rng& rng, int& flags) const {
     const Pair pxy = LoadPair(geo.posx_posy, i);
     const Pair pz  = LoadPair(geo.posz_pad, i);
     int vol        = geo.vol[i];
@@ -193,7 +198,15 @@ struct SlabGammaGeometryStep {
         bool doStop  = false;
         bool reached = false;
         double wdtStepLength = 0.0;
-        while (!doStop) {
+        // At most kWdtMaxVirtualSteps virtual steps per pass: a 0.2-1 MeV gamma crossing liquid argon with lead's cross
+        // section takes dozens, and a warp waits for its longest lane (171 ms per 4096 showers without the cap, 128 ms
+        // without Woodcock tracking at all).  A pass that is cut ends at a fictitious interaction point: the track is
+        // moved there, nothing else happens, and the next pass carries on with the next uniform of its stream --
+        // the exponential has no memory, so this is the uncut loop up to the rounding of the distance to the surface
+        // (recomputed from the new position instead of decremented).
+        int virtualSteps = 0;
+        while (!doStop && virtualSteps < kWdtMaxVirtualSteps) {
+          ++virtualSteps;
           const double pstep = wdtMFP < kDblMax ? -Log(rng.Flat()) * wdtMFP : kDblMax;
           if (distToBoundary < pstep) {
             wdtStepLength += distToBoundary;
@@ -226,6 +239,16 @@ struct SlabGammaGeometryStep {
         s.nIA0  = -1.0;
         physicalStep = reached ? 10.0 : 0.0;
         flags = reached ? (flags & ~static_cast<int>(G4HB200_F_WDT_ON)) : (flags | static_cast<int>(G4HB200_F_WDT_ON));
+        if (!doStop) {
+          // the pass was cut: the track waits at the fictitious interaction point for the next pass
+          StorePair(geo.posx_posy, i, pos[0], pos[1]);
+          StorePair(geo.posz_pad, i, pos[2], 0.0);
+          geo.vol[i]     = vol;
+          geo.nextVol[i] = vol;
+          s.gStep      = 0.0;
+          s.onBoundary = false;
+          return false;
+        }
       }
     }
     if (!wdt) {
@@ -247,6 +270,7 @@ struct SlabGammaGeometryStep {
     // the track keeps the normal step length only: zero after Woodcock tracking (TrackingManager.cc:1038-1046)
     s.gStep      = wdt ? 0.0 : step;
     s.onBoundary = onBoundary;
+    return true;
   }
 };
 

@@ -395,7 +395,11 @@ G4H_FN int ResampleNumIALeftWindow(double* nIA, const DrawWindow& dw) {
 struct NoGeometryStep {
   G4H_MFN void operator()(int64_t, ElectronState&, double) const {}
   // gamma: the step limit and what follows it up to SelectInteraction; flags: the track's flag bits (in / out)
-  G4H_MFN void GammaHowFarAndStep(const TablesView& tv, int64_t, GammaState& s, Rng& rng, int&) const { GammaHowFar(tv, s, rng); }
+  // returns false when the step ends without a boundary and without an interaction (a Woodcock pass that was cut)
+  G4H_MFN bool GammaHowFarAndStep(const TablesView& tv, int64_t, GammaState& s, Rng& rng, int&) const {
+    GammaHowFar(tv, s, rng);
+    return true;
+  }
 };
 // ... or a geometry step (g4h_shower.cuh: SlabGeometryStep) that shortens s.gStep and sets the post-step s.onBoundary.
 // returns the queue the track goes to next (kQFluct, kQDiscrete, kQAtRest, kQMscEl, kQMscPos) or -1
@@ -475,11 +479,17 @@ G4H_FN int StageGammaHead(const TablesView& tv, const G4HB200GammaBatch& b, int6
   LoadGamma(b, i, seed, s, rng);
   int flags = b.meta[4 * i + 1];
   if (kMode == 1) LoadGammaHandOver(b, i, s);
+  bool interacts = true;
   if (kMode == 2) {
-    geometry.GammaHowFarAndStep(tv, i, s, rng, flags);
+    interacts = geometry.GammaHowFarAndStep(tv, i, s, rng, flags);
     flags = s.onBoundary ? (flags | static_cast<int>(G4HB200_F_ON_BOUNDARY)) : (flags & ~static_cast<int>(G4HB200_F_ON_BOUNDARY));
   }
   int route = -1;
+  if (!interacts) {
+    s.edep = 0.0;
+    StoreGamma(b, i, s, rng, flags);
+    return -1;
+  }
   if (!s.onBoundary) {
     const double urnd = rng.Flat();
     s.nIA0 = -1.0;

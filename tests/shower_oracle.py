@@ -56,6 +56,7 @@ def uniform_at(seed, ids, draw):
 
 
 DBL_MAX = np.finfo(np.float64).max
+WDT_MAX_VIRTUAL_STEPS = 4  # kWdtMaxVirtualSteps of g4h_shower.cuh
 
 
 class Slab:
@@ -190,7 +191,7 @@ def _woodcock(reference, slab, calo, couple_material, gm, gm_pos, dirs, seed):
     vol = np.zeros(n, dtype=np.int32)
     gm.meta[:, 1] = np.where(on, gm.meta[:, 1], gm.meta[:, 1] & ~_capi.F_WDT_ON)
     if len(idx) == 0:
-        return on, phys, pos, vol
+        return on, phys, pos, vol, np.zeros(n, dtype=bool)
     m = len(idx)
     ek = ekin[idx]
     lek = gm.ekin_logekin[idx, 1]
@@ -213,7 +214,9 @@ def _woodcock(reference, slab, calo, couple_material, gm, gm_pos, dirs, seed):
     mfp0 = np.full(m, -1.0)
     d0 = dirs[idx, 0]
     x0 = gm_pos[idx, 0]
-    while not stop.all():
+    passes = 0
+    while not stop.all() and passes < WDT_MAX_VIRTUAL_STEPS:
+        passes += 1
         a = np.flatnonzero(~stop)
         need = wmfp[a] < DBL_MAX
         u = np.ones(len(a))
@@ -260,7 +263,9 @@ def _woodcock(reference, slab, calo, couple_material, gm, gm_pos, dirs, seed):
     gm.edep_pemxsec[idx, 1] = pe
     phys[idx] = np.where(reached, 10.0, 0.0)
     gm.meta[idx, 1] = np.where(reached, gm.meta[idx, 1] & ~_capi.F_WDT_ON, gm.meta[idx, 1] | _capi.F_WDT_ON)
-    return on, phys, pos, vol
+    cut = np.zeros(n, dtype=bool)
+    cut[idx] = ~stop  # the pass was cut after WDT_MAX_VIRTUAL_STEPS virtual steps: a fictitious interaction point
+    return on, phys, pos, vol, cut
 
 
 def run(reference, calo, num_primaries, primary_ekin, seed, kind=_capi.SEC_ELECTRON, first_track_id=0, max_steps=0, threads=4,
@@ -376,7 +381,7 @@ def run(reference, calo, num_primaries, primary_ekin, seed, kind=_capi.SEC_ELECT
         if gm.n > 0:
             dirs = np.stack([gm.dirx_diry[:, 0], gm.dirx_diry[:, 1], gm.dirz_nia0[:, 0]], axis=1)
             if getattr(calo, "woodcock", False):
-                wdt, phys, gm_pos, wvol = _woodcock(reference, slab, calo, np.asarray(couple_material), gm, gm_pos, dirs, seed)
+                wdt, phys, gm_pos, wvol, cut = _woodcock(reference, slab, calo, np.asarray(couple_material), gm, gm_pos, dirs, seed)
                 gm_vol = np.where(wdt, wvol, gm_vol).astype(np.int32)
                 normal = np.flatnonzero(~wdt)
                 if len(normal) > 0:
@@ -387,6 +392,7 @@ def run(reference, calo, num_primaries, primary_ekin, seed, kind=_capi.SEC_ELECT
                     phys[normal] = sub.gstep_mfp0[:, 0]
             else:
                 wdt = np.zeros(gm.n, dtype=bool)
+                cut = np.zeros(gm.n, dtype=bool)
                 reference.gamma_howfar(gm, seed, threads)
                 phys = gm.gstep_mfp0[:, 0].copy()
             dist, nv = slab.distance(gm_vol, gm_pos, dirs)
@@ -396,7 +402,18 @@ def run(reference, calo, num_primaries, primary_ekin, seed, kind=_capi.SEC_ELECT
             gm.gstep_mfp0[:, 0] = np.where(wdt, 0.0, step)
             gm.meta[:, 1] = np.where(onb, gm.meta[:, 1] | _capi.F_ON_BOUNDARY, gm.meta[:, 1] & ~_capi.F_ON_BOUNDARY)
             sec = batches.SecondaryHostQueue(2 * gm.n)
-            reference.gamma_perform(gm, sec, seed, threads)
+            if cut.any():
+                # a Woodcock pass that was cut: the track waits at a fictitious interaction point, nothing happens
+                go = np.flatnonzero(~cut)
+                sub = _take(gm, go, batches.GammaHostBatch)
+                reference.gamma_perform(sub, sec, seed, threads)
+                for g_ in sub.groups() + ("meta", "winner"):
+                    getattr(gm, g_)[go] = getattr(sub, g_)
+                nsec = int(sec.count[0])
+                sec.parent_slot[:nsec, 0] = go[sec.parent_slot[:nsec, 0]]
+                gm.edep_pemxsec[cut, 0] = 0.0
+            else:
+                reference.gamma_perform(gm, sec, seed, threads)
             np.add.at(hist, gm_vol, gm.edep_pemxsec[:, 0])
             new_vol = np.where(onb, nv, gm_vol)
             ekin = gm.ekin_logekin[:, 0]

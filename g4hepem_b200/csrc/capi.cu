@@ -960,8 +960,19 @@ int g4hb200_electron_lookups(G4HB200* h, int64_t n, const int32_t* imc, const do
   if (rc != 0) return rc;
   if (n < 0 || (n > 0 && (!imc || !ekin || !logekin || !out))) return Fail(G4HB200_EINVAL, "bad argument");
   if (n == 0) return 0;
-  ElectronLookupsKernel<<<OneWave(h, ElectronLookupsKernel, n), kThreadsPerBlock, 0, static_cast<cudaStream_t>(stream)>>>(
-      h->view, n, imc, ekin, logekin, is_electron ? 0 : 1, out);
+  const ElectronTablesView& ed = h->view.el[is_electron ? 0 : 1];
+  const size_t hot = reinterpret_cast<const char*>(ed.tr1Data + 2 * ed.numLoss * h->view.numMat) - reinterpret_cast<const char*>(ed.lossEGrid) + 16;
+  // the hot tables of one particle (66 KB for six couples) staged in shared memory, one 1024-thread CTA per SM: 7 %
+  // faster than gathering them through L1 (0.0583 -> 0.0546 ms per 1M look-up sets; G4HB200_LOOKUPS_SMEM=0: the L1 kernel)
+  const char* smemEnv = std::getenv("G4HB200_LOOKUPS_SMEM");
+  if (!(smemEnv != nullptr && smemEnv[0] == '0') && hot <= 200 * 1024) {
+    cudaFuncSetAttribute(ElectronLookupsSmemKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(hot));
+    ElectronLookupsSmemKernel<<<h->smCount, 1024, hot, static_cast<cudaStream_t>(stream)>>>(h->view, n, imc, ekin, logekin,
+                                                                                            is_electron ? 0 : 1, out);
+  } else {
+    ElectronLookupsKernel<<<OneWave(h, ElectronLookupsKernel, n), kThreadsPerBlock, 0, static_cast<cudaStream_t>(stream)>>>(
+        h->view, n, imc, ekin, logekin, is_electron ? 0 : 1, out);
+  }
   ++h->launches;
   G4H_CUDA(cudaGetLastError());
   return 0;

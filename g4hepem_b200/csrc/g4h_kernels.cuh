@@ -193,6 +193,50 @@ ElectronLookupsKernel(const __grid_constant__ TablesView tv, int64_t n, const in
   }
 }
 
+// the same with the particle's hot tables (loss, restricted cross sections, nuclear, transport: one contiguous block
+// of the arena) staged in shared memory: a look-up gathers 8 B from up to 32 different 32 B sectors of L1 per
+// instruction; shared memory serves scattered 8 B words at bank rate
+// the shared-memory copy of *p: the address is derived from the shared array, not from the global pointer (the
+// compiler picks the load instruction from the provenance of the address)
+template <class T>
+__device__ __forceinline__ const T* StagedPtr(const void* smemBase, const char* globalBase, const T* p) {
+  return reinterpret_cast<const T*>(static_cast<const char*>(smemBase) + (reinterpret_cast<const char*>(p) - globalBase));
+}
+
+__global__ void __launch_bounds__(1024, 1)
+ElectronLookupsSmemKernel(const __grid_constant__ TablesView tv, int64_t n, const int32_t* __restrict__ imc,
+                          const double* __restrict__ ekin, const double* __restrict__ lekin, int particle, double* __restrict__ out) {
+  extern __shared__ double2 smemTables[];
+  const ElectronTablesView& ed = tv.el[particle];
+  const char* lo = reinterpret_cast<const char*>(ed.lossEGrid);
+  const char* hi = reinterpret_cast<const char*>(ed.tr1Data + 2 * ed.numLoss * tv.numMat);
+  const int n16  = static_cast<int>((hi - lo + 15) / 16);
+  for (int k = threadIdx.x; k < n16; k += blockDim.x) smemTables[k] = __ldg(reinterpret_cast<const double2*>(lo) + k);
+  __syncthreads();
+  ElectronTablesView es = ed;
+  es.lossEGrid = StagedPtr(smemTables, lo, ed.lossEGrid);
+  es.lossData  = StagedPtr(smemTables, lo, ed.lossData);
+  es.resStart  = StagedPtr(smemTables, lo, ed.resStart);
+  es.resData   = StagedPtr(smemTables, lo, ed.resData);
+  es.enucEGrid = StagedPtr(smemTables, lo, ed.enucEGrid);
+  es.enucData  = StagedPtr(smemTables, lo, ed.enucData);
+  es.tr1Data   = StagedPtr(smemTables, lo, ed.tr1Data);
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const int c = imc[i];
+    const double e = ekin[i], le = lekin[i];
+    const int imat = __ldg(tv.mcImat + c);
+    const double range = RestRange(es, c, e, le);
+    out[0 * n + i] = range;
+    out[1 * n + i] = RestDEDX(es, c, e, le);
+    out[2 * n + i] = InvRange(es, c, range);
+    out[3 * n + i] = RestMacXSec(es, c, e, le, true);
+    out[4 * n + i] = RestMacXSec(es, c, e, le, false);
+    out[5 * n + i] = MacXSecNuclear(es, imat, e, le);
+    out[6 * n + i] = TransportMFP(es, imat, e, le);
+  }
+}
+
 __global__ void __launch_bounds__(kThreadsPerBlock)
 ElectronSteppingXSecsKernel(const __grid_constant__ TablesView tv, int64_t n, const int32_t* __restrict__ imc,
                             const double* __restrict__ ekin, const double* __restrict__ lekin, int particle,

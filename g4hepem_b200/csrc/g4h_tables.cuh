@@ -80,7 +80,9 @@ enum ElemPar { kEZet = 0, kEZet13, kEZet23, kECoulomb, kELogZ, kEZFactor1, kEDel
 enum CutPar { kCElCut = 0, kCPosCut, kCGamCut, kCLogGamCut };
 
 #if defined(__CUDA_ARCH__)
-#define G4H_LD(p) __ldg(p)
+// plain loads: the compiler emits LDG for pointers it can trace to a kernel parameter and LDS / generic loads for the
+// shared-memory copies of the tables (ElectronLookupsSmemKernel); __ldg would be invalid for the latter
+#define G4H_LD(p) (*(p))
 #else
 #define G4H_LD(p) (*(p))
 #endif

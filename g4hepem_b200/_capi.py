@@ -209,6 +209,7 @@ PROTOTYPES = {
     "g4hb200_secondary_queue_download": (C.c_int, [_H, C.POINTER(SecondaryQueue), C.POINTER(SecondaryQueue), _vp]),
     "g4hb200_sync": (C.c_int, [_H, _vp]),
     "g4hb200_electron_lookups": (C.c_int, [_H, C.c_int64, _vp, _vp, _vp, C.c_int, _vp, _vp]),
+    "g4hb200_electron_lookups_f32": (C.c_int, [_H, C.c_int64, _vp, _vp, _vp, C.c_int, _vp, _vp]),
     "g4hb200_electron_stepping_xsecs": (C.c_int, [_H, C.c_int64, _vp, _vp, _vp, C.c_int, _vp, _vp]),
     "g4hb200_gamma_lookups": (C.c_int, [_H, C.c_int64, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "g4hb200_select_target_element": (C.c_int, [_H, C.c_int, C.c_int, C.c_int64, _vp, _vp, _vp, _vp, _vp, _vp]),

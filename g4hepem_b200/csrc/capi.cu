@@ -14,6 +14,7 @@
 #include "../../include/g4hepem_b200.h"
 #include "g4h_kernels.cuh"
 #include "g4h_pipeline.cuh"
+#include "g4h_lookups_f32.cuh"
 #include "g4h_shower.cuh"
 #include "g4h_view.cuh"
 
@@ -973,6 +974,31 @@ int g4hb200_electron_lookups(G4HB200* h, int64_t n, const int32_t* imc, const do
     ElectronLookupsKernel<<<OneWave(h, ElectronLookupsKernel, n), kThreadsPerBlock, 0, static_cast<cudaStream_t>(stream)>>>(
         h->view, n, imc, ekin, logekin, is_electron ? 0 : 1, out);
   }
+  ++h->launches;
+  G4H_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int g4hb200_electron_lookups_f32(G4HB200* h, int64_t n, const int32_t* imc, const float* ekin, const float* logekin,
+                                 int is_electron, float* out, void* stream) {
+  int rc = CheckHandle(h);
+  if (rc != 0) return rc;
+  if (n < 0 || (n > 0 && (!imc || !ekin || !logekin || !out))) return Fail(G4HB200_EINVAL, "bad argument");
+  if (n == 0) return 0;
+  const ElectronTablesView& ed = h->view.el[is_electron ? 0 : 1];
+  LookupsF32Layout lay;
+  lay.lossEGrid = 0;
+  lay.lossData  = static_cast<int>(ed.lossData - ed.lossEGrid);
+  lay.resData   = static_cast<int>(ed.resData - ed.lossEGrid);
+  lay.enucEGrid = static_cast<int>(ed.enucEGrid - ed.lossEGrid);
+  lay.enucData  = static_cast<int>(ed.enucData - ed.lossEGrid);
+  lay.tr1Data   = static_cast<int>(ed.tr1Data - ed.lossEGrid);
+  lay.total     = lay.tr1Data + 2 * ed.numLoss * h->view.numMat;
+  const size_t bytes = (static_cast<size_t>(lay.total) + h->view.numMatCut) * sizeof(float);
+  if (bytes > 200 * 1024) return Fail(G4HB200_EINVAL, "table set too large for the shared-memory look-up kernel");
+  G4H_CUDA(cudaFuncSetAttribute(ElectronLookupsF32Kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(bytes)));
+  ElectronLookupsF32Kernel<<<h->smCount, 1024, bytes, static_cast<cudaStream_t>(stream)>>>(h->view, lay, n, imc, ekin, logekin,
+                                                                                         is_electron ? 0 : 1, out);
   ++h->launches;
   G4H_CUDA(cudaGetLastError());
   return 0;

@@ -80,6 +80,15 @@ class Engine:
                                                       int(is_electron), out.data_ptr(), _stream_ptr()), "electron_lookups")
         return out
 
+    def electron_lookups_f32(self, imc, ekin, logekin, is_electron=True):
+        """single precision variant (float32 tensors in, (7, n) float32 out): stated bound 2e-5 relative"""
+        torch = _torch()
+        n = imc.numel()
+        out = torch.empty((7, n), dtype=torch.float32, device=imc.device)
+        _capi.check(self.lib.g4hb200_electron_lookups_f32(self.handle, n, imc.data_ptr(), ekin.data_ptr(), logekin.data_ptr(),
+                                                          int(is_electron), out.data_ptr(), _stream_ptr()), "electron_lookups_f32")
+        return out
+
     def electron_lookups_into(self, imc, ekin, logekin, out, is_electron=True):
         _capi.check(self.lib.g4hb200_electron_lookups(self.handle, imc.numel(), imc.data_ptr(), ekin.data_ptr(), logekin.data_ptr(),
                                                       int(is_electron), out.data_ptr(), _stream_ptr()), "electron_lookups")

@@ -227,6 +227,16 @@ int g4hb200_sync(G4HB200* h, void* stream);
  * out is 7 arrays of n doubles: out[k*n + i]. is_electron selects e- / e+ tables. */
 int g4hb200_electron_lookups(G4HB200* h, int64_t n, const int32_t* imc, const double* ekin, const double* logekin,
                              int is_electron, double* out, void* stream);
+/* The same seven look-ups in single precision on a float copy of the tables (float device arrays in and out):
+ * |f32 - f64| <= 2e-5 |f64| + 1e-6 max|f64| per output over a batch (measured on the configs[0] inputs: 4e-6 relative;
+ * 2.5e-8 of the maximum right above a production threshold) for couples whose table entries and their squares fit in
+ * single precision (everything but the vacuum couple, whose ranges exceed 1e19 mm); 1.9x the FP64 rate
+ * (3.9e10 look-up sets/s on a B200) -- a stated bound, not bit identity; the FP64
+ * entry point above is the drop-in.
+ * (The reference's authors note that parts of this path "could probably be computed in float",
+ * G4HepEmElectronInteractionUMSC.icc:296,312.) */
+int g4hb200_electron_lookups_f32(G4HB200* h, int64_t n, const int32_t* imc, const float* ekin, const float* logekin,
+                                 int is_electron, float* out, void* stream);
 /* G4HepEmElectronManager::GetRestMacXSecForStepping (ioni, brem), GetMacXSecNuclearForStepping,
  * ComputeMacXsecAnnihilationForStepping (.icc:544-599): out[k*n+i], k = 0..3 */
 int g4hb200_electron_stepping_xsecs(G4HB200* h, int64_t n, const int32_t* imc, const double* ekin, const double* logekin,

@@ -376,3 +376,28 @@ def test_half_batch_pipelines_do_not_change_the_result(engine, flat_tables):
         for k in ("ekin", "kind", "parent_id"):
             assert np.array_equal(x[k][ox], y[k][oy]), k
         assert np.array_equal(x["dir"][ox], y["dir"][oy])
+
+
+@pytest.mark.parametrize("is_electron", [True, False])
+def test_electron_lookups_f32_bound(engine, flat_tables, is_electron):
+    """The single precision variant of the configs[0] look-ups (g4hb200_electron_lookups_f32) against the FP64 entry
+    point on the same inputs: the stated bound is |f32 - f64| <= 2e-5 |f64| + 1e-6 max|f64| (measured: 4e-6 relative; cross sections right above
+    their production threshold, 1e-4 of the maximum, lose digits to cancellation: 2.5e-8 of the maximum)."""
+    import torch
+
+    rng = np.random.default_rng(0)
+    n = 1 << 20
+    # couple 0 is the vacuum ("Galactic"): its ranges (> 1e19 mm) square to more than single precision holds, the
+    # bound is stated for the material couples
+    imc = rng.integers(1, flat_tables.num_matcut, n).astype(np.int32)
+    ek32 = np.exp(rng.uniform(np.log(0.95e-4), np.log(1.02e8), n)).astype(np.float32)
+    lek32 = np.log(ek32.astype(np.float64)).astype(np.float32)
+    want = engine.electron_lookups(_cuda(imc), _cuda(ek32.astype(np.float64)), _cuda(np.log(ek32.astype(np.float64))),
+                                   is_electron).cpu().numpy()
+    got = engine.electron_lookups_f32(_cuda(imc), _cuda(ek32), _cuda(lek32), is_electron).cpu().numpy().astype(np.float64)
+    torch.cuda.synchronize()
+    for k in range(7):
+        scale = np.abs(want[k]).max()
+        tol = 2e-5 * np.abs(want[k]) + 1e-6 * scale
+        bad = np.abs(got[k] - want[k]) > tol
+        assert not bad.any(), (k, int(bad.sum()), float(np.abs(got[k] - want[k])[bad].max()), float(want[k][bad][0]), float(got[k][bad][0]))

@@ -620,6 +620,16 @@ G4H_FN void PerformCompton(GammaState& s, Rng& rng, Secondaries& sec) {
   s.edep = theEnergyDeposit;
 }
 
+// std::pow(x, 1./3.) of Conversion.icc:188,216 for x in (0, 1): the cube root (libdevice's cbrt is a quarter of the
+// instructions of its pow; the two differ from the host's pow by an ulp either way, well inside the 1e-12 of energies)
+G4H_FN double CubeRoot(double x) {
+#if defined(__CUDA_ARCH__)
+  return cbrt(x);
+#else
+  return pow(x, 1. / 3.);
+#endif
+}
+
 // Conversion screening functions (Conversion.icc:237-273)
 G4H_FN double ScreenFunction1(double delta) {
   return (delta > 1.4) ? 42.038 - 8.29 * Log(delta + 0.958) : 42.184 - delta * (7.444 - 1.623 * delta);
@@ -683,28 +693,28 @@ G4H_FN void ConversionSampleKinEnergies(const TablesView& tv, double thePrimEkin
       const double r0 = rng.Flat();
       const double r1 = rng.Flat();
       r2 = rng.Flat();
-      if (NormCond > r0) {
-        eps = 0.5 - epsRange * pow(r1, 1. / 3.);
-        const double delta = deltaFactor / (eps * (1. - eps));
-        if (!withLPM) {
-          greject = (ScreenFunction1(delta) - FZ) * invF10;
-        } else {
-          double funcXiS, funcGS, funcPhiS, phi1, phi2;
-          ComputePhi12(delta, phi1, phi2);
-          EvaluateLPMFunctions(funcXiS, funcGS, funcPhiS, thePrimEkin, eps * thePrimEkin, lpmEnr, z23, ilVarS1, ilVarS1Cond, 0.0, -1.0);
-          greject = funcXiS * ((2. * funcPhiS + funcGS) * phi1 - funcGS * phi2 - funcPhiS * FZ) * invF10;
-        }
+      // one call site for what the four branches of the reference share (Conversion.icc:196-231): the screening
+      // variable, its logarithm (ScreenFunction1/2 and ComputePhi12 take the same Log(delta + 0.958) above 1.4) and
+      // the LPM functions; the branches then only combine them.  (Called from the four branches the logarithm ran
+      // at 6 of 32 lanes and was a sixth of the kernel's instructions.)
+      const bool first = NormCond > r0;
+      eps = first ? 0.5 - epsRange * CubeRoot(r1) : epsMin + epsRange * r1;
+      const double delta    = deltaFactor / (eps * (1. - eps));
+      const bool highDelta  = delta > 1.4;
+      const double logDelta = Log(highDelta ? delta + 0.958 : 1.0);
+      if (!withLPM) {
+        // ScreenFunction1 / ScreenFunction2 (Conversion.icc:237-248)
+        const double screen = highDelta ? 42.038 - 8.29 * logDelta
+                                        : (first ? 42.184 - delta * (7.444 - 1.623 * delta) : 41.326 - delta * (5.848 - 0.902 * delta));
+        greject = (screen - FZ) * (first ? invF10 : invF20);
       } else {
-        eps = epsMin + epsRange * r1;
-        const double delta = deltaFactor / (eps * (1. - eps));
-        if (!withLPM) {
-          greject = (ScreenFunction2(delta) - FZ) * invF20;
-        } else {
-          double funcXiS, funcGS, funcPhiS, phi1, phi2;
-          ComputePhi12(delta, phi1, phi2);
-          EvaluateLPMFunctions(funcXiS, funcGS, funcPhiS, thePrimEkin, eps * thePrimEkin, lpmEnr, z23, ilVarS1, ilVarS1Cond, 0.0, -1.0);
-          greject = funcXiS * ((funcPhiS + 0.5 * funcGS) * phi1 + 0.5 * funcGS * phi2 - 0.5 * (funcGS + funcPhiS) * FZ) * invF20;
-        }
+        // ComputePhi12 (Conversion.icc:250-262)
+        const double phi1 = highDelta ? 21.0190 - 4.145 * logDelta : 20.806 - delta * (3.190 - 0.5710 * delta);
+        const double phi2 = highDelta ? phi1 : 20.234 - delta * (2.126 - 0.0903 * delta);
+        double funcXiS, funcGS, funcPhiS;
+        EvaluateLPMFunctions(funcXiS, funcGS, funcPhiS, thePrimEkin, eps * thePrimEkin, lpmEnr, z23, ilVarS1, ilVarS1Cond, 0.0, -1.0);
+        greject = first ? funcXiS * ((2. * funcPhiS + funcGS) * phi1 - funcGS * phi2 - funcPhiS * FZ) * invF10
+                        : funcXiS * ((funcPhiS + 0.5 * funcGS) * phi1 + 0.5 * funcGS * phi2 - 0.5 * (funcGS + funcPhiS) * FZ) * invF20;
       }
     } while (greject < r2);
   }

@@ -133,6 +133,58 @@ class ClockSampler:
         return out
 
 
+class NvmlClockSampler:
+    """SM clock and throttle reasons polled in-process through NVML every ~1 ms: the timed region of the default run is
+    ~10 ms, which `nvidia-smi -lms 100` (ClockSampler, the fallback) sees once at best."""
+
+    def __init__(self, index):
+        import threading
+
+        import pynvml
+
+        self.nv = pynvml
+        pynvml.nvmlInit()
+        self.handle = pynvml.nvmlDeviceGetHandleByIndex(index)
+        self.smax = float(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM))
+        self.samples = []
+        self.reasons = 0
+        self.running = True
+        self.thread = threading.Thread(target=self._poll, daemon=True)
+        self.thread.start()
+
+    def _poll(self):
+        nv = self.nv
+        get_reasons = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or nv.nvmlDeviceGetCurrentClocksThrottleReasons
+        while self.running:
+            try:
+                self.samples.append(float(nv.nvmlDeviceGetClockInfo(self.handle, nv.NVML_CLOCK_SM)))
+                self.reasons |= int(get_reasons(self.handle))
+            except nv.NVMLError:
+                pass
+            time.sleep(0.001)
+
+    def stop(self):
+        self.running = False
+        self.thread.join(timeout=2)
+        nv = self.nv
+        names = {"hw_slowdown": 0x8, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4}
+        out = {"sm_mhz": float(np.median(self.samples)) if self.samples else None, "sm_max_mhz": self.smax,
+               "reasons": sorted(k for k, bit in names.items() if self.reasons & bit), "samples": len(self.samples),
+               "source": "nvml, 1 ms poll over the timed region"}
+        try:
+            nv.nvmlShutdown()
+        except nv.NVMLError:
+            pass
+        return out
+
+
+def make_clock_sampler(index):
+    try:
+        return NvmlClockSampler(index)
+    except Exception:  # no pynvml / no NVML: fall back to the nvidia-smi poller
+        return ClockSampler(index)
+
+
 def _dist_env():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -243,7 +295,7 @@ def run_gpu(args):
         eng.ElectronManager.Step(engine, ring[i % ring_n], sec, SEED)
     barrier()
     launches0 = engine.launch_count
-    sampler = ClockSampler(local) if rank == 0 else None
+    sampler = make_clock_sampler(local) if rank == 0 else None
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
     barrier()
@@ -256,6 +308,7 @@ def run_gpu(args):
         kev[i][1].record()
     ev1.record()
     barrier()
+    clocks = sampler.stop() if sampler is not None else None
     elapsed_ms = ev0.elapsed_time(ev1)
     kernel_ms = float(np.mean([a.elapsed_time(b) for a, b in kev]))
     n_sec = int(sec.count[0].item())
@@ -275,7 +328,6 @@ def run_gpu(args):
     torch.cuda.synchronize()
     stage_times = engine.kernel_times()
     engine.set_kernel_timing(False)
-    clocks = sampler.stop() if sampler is not None else None
     if dist is not None:
         t = torch.tensor([elapsed_ms], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)

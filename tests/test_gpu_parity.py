@@ -401,3 +401,16 @@ def test_electron_lookups_f32_bound(engine, flat_tables, is_electron):
         tol = 2e-5 * np.abs(want[k]) + 1e-6 * scale
         bad = np.abs(got[k] - want[k]) > tol
         assert not bad.any(), (k, int(bad.sum()), float(np.abs(got[k] - want[k])[bad].max()), float(want[k][bad][0]), float(got[k][bad][0]))
+
+
+def test_electron_fused_step_with_odd_draw_counters(engine, reference, flat_tables):
+    """Fresh tracks whose streams stand at an odd draw: the fused head needs the sixth uniform of its window from a
+    fourth Philox block (DrawWindow::Sixth), the MSC stage reads its window one slot later."""
+    n = 100000
+    host = batches.make_electron_batch(n, flat_tables.num_matcut, seed=21)
+    host.meta[:, 3] = 2 * np.arange(n, dtype=np.int32) % 1000 + 1
+    want = host.copy()
+    qwant = batches.SecondaryHostQueue(2 * n)
+    reference.electron_step(want, qwant, SEED, 8)
+    got, sec = _run_gpu_electron(engine, host, "step")
+    _assert_electron(want, got, qwant, sec.download(), handover=False)

@@ -91,3 +91,18 @@ def test_electron_fused_step_staged(sim, reference, flat_tables):
         for x in (a, b):
             x.ekin_logekin[dead, 0] = 1.0
             x.ekin_logekin[dead, 1] = 100.0
+
+
+def test_fused_step_with_odd_draw_counters(sim, reference, flat_tables):
+    """Fresh tracks (all four interaction lengths resampled) whose streams stand at an odd draw: the head stage then
+    needs the sixth uniform of its window from a fourth Philox block (DrawWindow::Sixth)."""
+    n = 20000
+    a = batches.make_electron_batch(n, flat_tables.num_matcut, seed=21)
+    a.meta[:, 3] = 2 * np.arange(n, dtype=np.int32) % 1000 + 1
+    b = a.copy()
+    qa, qb = batches.SecondaryHostQueue(2 * n), batches.SecondaryHostQueue(2 * n)
+    reference.electron_step(a, qa, 2026, 4)
+    sim.electron_step_staged(b, qb, 2026)
+    rep = compare.compare_electron_batches(a, b, handover=False)
+    assert compare.total_bad(rep) == 0, compare.format_report(rep, True)
+    assert compare.total_bad(compare.compare_secondaries(qa, qb)) == 0

@@ -18,4 +18,10 @@ gd.upload(g); eng.GammaManager.Step(e, gd, gs, 2026); torch.cuda.synchronize()
 for w in (False, True):
     r = shower.run(e, shower.SlabCalorimeter(woodcock=w), 4, 200.0, 2026, capacity=1 << 15)
     print("shower", w, r.stats["num_steps"], float(r.edep.sum()))
+imc = torch.from_numpy(np.random.default_rng(1).integers(1, ft.num_matcut, n).astype(np.int32)).cuda()
+ek = torch.from_numpy(np.exp(np.random.default_rng(2).uniform(np.log(1e-4), np.log(1e8), n))).cuda()
+r64 = e.electron_lookups(imc, ek, torch.log(ek), True)
+r32 = e.electron_lookups_f32(imc, ek.float(), torch.log(ek).float(), False)
+torch.cuda.synchronize()
+print("lookups", float(r64[0].sum()), float(r32[0].double().sum()))
 print("done")

@@ -107,7 +107,7 @@ ELECTRON_PAIR_GROUPS = (
     "ekin_logekin", "dirx_diry", "dirz_safety", "nia01", "nia23", "msc_irange_dynrf", "msc_tlimmin_gauss",
 )
 ELECTRON_RESULT_GROUPS = ("gstep_pstep", "edep_dispx", "dispy_dispz")
-ELECTRON_HANDOVER_GROUPS = ("mfp01", "mfp23", "range_lambtr1", "tstep_zpath", "par12", "par3_pad")
+ELECTRON_HANDOVER_GROUPS = ("mfp01", "mfp23", "range_lambtr1", "tstep_zpath", "par12", "par3_pad", "prestep")
 
 
 class ElectronBatch(C.Structure):
@@ -185,6 +185,10 @@ F_GAUSS_CACHED = 0x40
 F_WDT_ON = 0x80
 
 SEC_ELECTRON, SEC_POSITRON, SEC_GAMMA = 0, 1, 2
+# op codes of g4hb200_electron_track_op / g4hb200_gamma_track_op (include/g4hepem_b200.h)
+(OP_HOWFAR_DISCRETE, OP_HOWFAR_MSC, OP_UPDATE_PSTEP, OP_UPDATE_NIA, OP_MEAN_ELOSS, OP_SAMPLE_MSC, OP_LOSS_FLUCT, OP_DISCRETE,
+ OP_ANNIHILATE_AT_REST, OP_PERFORM_CONTINUOUS, OP_RESAMPLE_NIA) = range(11)
+GOP_HOWFAR_TRACK, GOP_UPDATE_NIA, GOP_SELECT_INTERACTION, GOP_PERFORM_SELECTED = range(4)
 NUM_STAGES = 20
 
 # every symbol include/g4hepem_b200.h declares: name -> (restype, argtypes)
@@ -208,6 +212,9 @@ PROTOTYPES = {
     "g4hb200_gamma_batch_download": (C.c_int, [_H, C.POINTER(GammaBatch), C.POINTER(GammaBatch), _vp]),
     "g4hb200_secondary_queue_download": (C.c_int, [_H, C.POINTER(SecondaryQueue), C.POINTER(SecondaryQueue), _vp]),
     "g4hb200_sync": (C.c_int, [_H, _vp]),
+    "g4hb200_device_alloc": (C.c_int, [_H, C.c_size_t, C.POINTER(_vp)]),
+    "g4hb200_device_free": (C.c_int, [_H, _vp]),
+    "g4hb200_memcpy": (C.c_int, [_H, _vp, _vp, C.c_size_t, C.c_int, _vp]),
     "g4hb200_electron_lookups": (C.c_int, [_H, C.c_int64, _vp, _vp, _vp, C.c_int, _vp, _vp]),
     "g4hb200_electron_lookups_f32": (C.c_int, [_H, C.c_int64, _vp, _vp, _vp, C.c_int, _vp, _vp]),
     "g4hb200_electron_stepping_xsecs": (C.c_int, [_H, C.c_int64, _vp, _vp, _vp, C.c_int, _vp, _vp]),
@@ -221,6 +228,9 @@ PROTOTYPES = {
     "g4hb200_gamma_howfar": (C.c_int, [_H, C.POINTER(GammaBatch), C.c_uint64, _vp]),
     "g4hb200_gamma_perform": (C.c_int, [_H, C.POINTER(GammaBatch), C.POINTER(SecondaryQueue), C.c_uint64, _vp]),
     "g4hb200_gamma_step": (C.c_int, [_H, C.POINTER(GammaBatch), C.POINTER(SecondaryQueue), C.c_uint64, _vp]),
+    "g4hb200_electron_track_op": (C.c_int, [_H, C.c_int, C.POINTER(ElectronBatch), C.POINTER(SecondaryQueue), C.c_uint64, _vp, _vp]),
+    "g4hb200_electron_check_delta": (C.c_int, [_H, C.POINTER(ElectronBatch), _vp, _vp, _vp]),
+    "g4hb200_gamma_track_op": (C.c_int, [_H, C.c_int, C.POINTER(GammaBatch), C.POINTER(SecondaryQueue), C.c_uint64, _vp]),
     "g4hb200_electron_step_host": (C.c_int, [_H, C.POINTER(ElectronBatch), C.POINTER(SecondaryQueue), C.c_uint64]),
     "g4hb200_gamma_step_host": (C.c_int, [_H, C.POINTER(GammaBatch), C.POINTER(SecondaryQueue), C.c_uint64]),
     "g4hb200_launch_count": (C.c_int64, [_H]),

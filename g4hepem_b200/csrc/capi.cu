@@ -14,8 +14,10 @@
 #include "../../include/g4hepem_b200.h"
 #include "g4h_kernels.cuh"
 #include "g4h_pipeline.cuh"
+#include "g4h_fused.cuh"
 #include "g4h_lookups_f32.cuh"
 #include "g4h_shower.cuh"
+#include "g4h_trackops.cuh"
 #include "g4h_view.cuh"
 
 using namespace g4h;
@@ -125,6 +127,8 @@ struct G4HB200 {
   int32_t* chunkCounters = nullptr;  // device, [kMaxChunks]
   static constexpr int kMaxChunks = 256;
   bool monolith = false;  // G4HB200_MONOLITH=1: the one-kernel-per-step variant (kept for A/B measurements)
+  bool fused = true;      // the step as one persistent launch with CTA-local queues (g4h_fused.cuh); G4HB200_FUSED=0: the
+                          // round-1 pipeline of stage kernels over global queues (kept for A/B measurements)
   // device batches of at least this many tracks run as two half-batch pipelines side by side (G4HB200_SPLIT_MIN)
   int64_t splitThreshold = 1 << 18;
   int splitParts = 2;  // G4HB200_SPLIT_PARTS, at most kNumSlots
@@ -170,11 +174,12 @@ int DevAlloc(T*& p, size_t count) {
   return 0;
 }
 
-void ElectronDoubleGroups(G4HB200ElectronBatch* b, double** out[16]) {
-  double** g[16] = {&b->ekin_logekin, &b->dirx_diry, &b->dirz_safety, &b->nia01, &b->nia23, &b->msc_irange_dynrf,
-                    &b->msc_tlimmin_gauss, &b->gstep_pstep, &b->edep_dispx, &b->dispy_dispz, &b->mfp01, &b->mfp23,
-                    &b->range_lambtr1, &b->tstep_zpath, &b->par12, &b->par3_pad};
-  for (int i = 0; i < 16; ++i) out[i] = g[i];
+constexpr int kNumElGroups = 17;  // double-pair groups of G4HB200ElectronBatch
+void ElectronDoubleGroups(G4HB200ElectronBatch* b, double** out[kNumElGroups]) {
+  double** g[kNumElGroups] = {&b->ekin_logekin, &b->dirx_diry, &b->dirz_safety, &b->nia01, &b->nia23, &b->msc_irange_dynrf,
+                              &b->msc_tlimmin_gauss, &b->gstep_pstep, &b->edep_dispx, &b->dispy_dispz, &b->mfp01, &b->mfp23,
+                              &b->range_lambtr1, &b->tstep_zpath, &b->par12, &b->par3_pad, &b->prestep};
+  for (int i = 0; i < kNumElGroups; ++i) out[i] = g[i];
 }
 
 void GammaDoubleGroups(G4HB200GammaBatch* b, double** out[5]) {
@@ -191,8 +196,8 @@ int CopyGroup(void* dst, const void* src, size_t bytes, cudaMemcpyKind kind, cud
 int CopyElectron(const G4HB200ElectronBatch* from, G4HB200ElectronBatch* to, cudaMemcpyKind kind, cudaStream_t st,
                  int firstGroup, int lastGroup, bool withMeta, bool withWinner) {
   const int64_t n = from->n;
-  double** gf[16];
-  double** gt[16];
+  double** gf[kNumElGroups];
+  double** gt[kNumElGroups];
   ElectronDoubleGroups(const_cast<G4HB200ElectronBatch*>(from), gf);
   ElectronDoubleGroups(to, gt);
   for (int i = firstGroup; i < lastGroup; ++i) {
@@ -304,19 +309,19 @@ int EnsureElectronWork(G4HB200::WorkSlot& slot, int64_t n) {
 // pipeline stages of the e-/e+ step, in launch order (g4h_pipeline.cuh)
 enum ElStage {
   kSHowFarXS = 0, kSHowFarMSC, kSAlongStep, kSStepHead, kSMscEl, kSMscPos, kSFluct, kSDiscrete, kSMoller, kSBhabha, kSSB, kSRB,
-  kSAnnih, kSAtRest, kSGammaHead, kSGammaConversion, kSGammaCompton, kSGammaPhotoelectric,
+  kSAnnih, kSAtRest, kSGammaHead, kSGammaConversion, kSGammaCompton, kSGammaPhotoelectric, kSElFused, kSGammaFused,
   kNumElStages
 };
 static_assert(kNumElStages <= G4HB200_NUM_STAGES, "G4HB200_NUM_STAGES too small");
 // pipeline stage -> queue that feeds it (-1: every track of the batch)
 const int kStageQueue[G4HB200_NUM_STAGES] = {-1, -1, -1, -1, kQMscEl, kQMscPos, kQFluct, kQDiscrete, kQMoller, kQBhabha, kQSB,
-                                             kQRB, kQAnnih, kQAtRest, -1, kGQConversion, kGQCompton, kGQPhotoelectric};
+                                             kQRB, kQAnnih, kQAtRest, -1, kGQConversion, kGQCompton, kGQPhotoelectric, -1, -1};
 const char* const kStageName[G4HB200_NUM_STAGES] = {
     "ElHowFarXSKernel", "ElHowFarMSCKernel", "ElAlongStepKernel", "ElStepHeadKernel", "ElMSCSampleKernel<e->",
     "ElMSCSampleKernel<e+>", "ElFluctuationKernel", "ElDiscreteKernel",
     "ElSamplerKernel<Moller>", "ElSamplerKernel<Bhabha>", "ElSamplerKernel<SeltzerBerger>", "ElSamplerKernel<RelBrem>",
     "ElSamplerKernel<Annihilation>", "ElSamplerKernel<AtRest>", "GammaHeadKernel", "GammaInteractKernel<Conversion>",
-    "GammaInteractKernel<Compton>", "GammaInteractKernel<Photoelectric>"};
+    "GammaInteractKernel<Compton>", "GammaInteractKernel<Photoelectric>", "ElFusedStepKernel", "GammaFusedStepKernel"};
 
 struct StageTimer {
   G4HB200* h;
@@ -540,12 +545,116 @@ int LaunchGammaPipeline(G4HB200* h, G4HB200GammaBatch* dev, G4HB200SecondaryQueu
   return 0;
 }
 
+
+// A sub-range of a batch (same struct, pointers advanced).
+G4HB200ElectronBatch ElectronBatchView(const G4HB200ElectronBatch& full, int64_t lo, int64_t len);
+G4HB200GammaBatch GammaBatchView(const G4HB200GammaBatch& full, int64_t lo, int64_t len);
+
+// One wave of the fused kernels: SM count x occupancy CTAs, never more than there are tiles
+template <class K>
+int FusedGrid(G4HB200* h, K kernel, int64_t n) {
+  const void* key = reinterpret_cast<const void*>(kernel);
+  auto it = h->residentCtas.find(key);
+  if (it == h->residentCtas.end()) {
+    int perSM = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, kernel, kThreadsPerBlock, 0) != cudaSuccess || perSM < 1) perSM = 1;
+    it = h->residentCtas.emplace(key, perSM).first;
+  }
+  const int64_t tiles = (n + kThreadsPerBlock - 1) / kThreadsPerBlock;
+  const int64_t full  = static_cast<int64_t>(h->smCount) * it->second;
+  return static_cast<int>(tiles < full ? (tiles > 0 ? tiles : 1) : full);
+}
+
+// The e-/e+ step (kPerformOnly: Perform alone) as one persistent launch (g4h_fused.cuh); a batch of more tiles than
+// one wave can index with 16-bit queue entries (19M tracks on a B200) goes in several launches.
+template <bool kPerformOnly>
+int LaunchElectronFused(G4HB200* h, G4HB200ElectronBatch* dev, G4HB200SecondaryQueue* sec, uint64_t seed, void* stream,
+                        const SlabHead* slab = nullptr, int slotIndex = 0) {
+  int rc = CheckHandle(h);
+  if (rc != 0) return rc;
+  if (dev == nullptr || dev->n < 0) return Fail(G4HB200_EINVAL, "bad electron batch");
+  if (sec == nullptr) return Fail(G4HB200_EINVAL, "secondary queue required");
+  if (dev->n == 0) return 0;
+  if (dev->n > 0x7fffffff) return Fail(G4HB200_EINVAL, "batch too large (track indices are 32 bit)");
+  if ((rc = EnsureElectronWork(h->slots[slotIndex], dev->n)) != 0) return rc;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  StageTimer t{h, st};
+  G4H_CUDA(t.Begin(dev->n));
+  const int fullGrid = FusedGrid(h, ElFusedStepKernel<kPerformOnly>, dev->n);
+  const int64_t perLaunch = static_cast<int64_t>(fullGrid) * kFusedMaxTilesPerCta * kThreadsPerBlock;
+  G4H_CUDA(t.Before(kSElFused));
+  for (int64_t lo = 0; lo < dev->n; lo += perLaunch) {
+    const int64_t len = dev->n - lo < perLaunch ? dev->n - lo : perLaunch;
+    G4HB200ElectronBatch part = ElectronBatchView(*dev, lo, len);
+    G4HB200SecondaryQueue q = *sec;
+    q.parent_base = sec->parent_base + static_cast<int32_t>(lo);
+    double* prestep = h->slots[slotIndex].work.prestep + 2 * lo;
+    if (slab != nullptr) {
+      TrackGeo geo = slab->geo;
+      geo.posx_posy += 2 * lo;
+      geo.posz_pad += 2 * lo;
+      geo.vol += lo;
+      geo.nextVol += lo;
+      ShowerElectronFusedKernel<<<FusedGrid(h, ShowerElectronFusedKernel, len), kThreadsPerBlock, 0, st>>>(h->view, part, prestep, q, seed,
+                                                                                                       slab->g, geo);
+    } else {
+      ElFusedStepKernel<kPerformOnly><<<FusedGrid(h, ElFusedStepKernel<kPerformOnly>, len), kThreadsPerBlock, 0, st>>>(h->view, part, prestep,
+                                                                                                                 q, seed);
+    }
+    ++h->launches;
+  }
+  --h->launches;  // After() counts one
+  G4H_CUDA(t.After(kSElFused));
+  if (t.tc != nullptr) G4H_CUDA(cudaEventRecord(t.tc->done, st));
+  G4H_CUDA(cudaGetLastError());
+  return 0;
+}
+
+template <int kMode>
+int LaunchGammaFused(G4HB200* h, G4HB200GammaBatch* dev, G4HB200SecondaryQueue* sec, uint64_t seed, void* stream,
+                     const SlabHead* slab = nullptr) {
+  int rc = CheckHandle(h);
+  if (rc != 0) return rc;
+  if (dev == nullptr || dev->n < 0) return Fail(G4HB200_EINVAL, "bad gamma batch");
+  if (sec == nullptr) return Fail(G4HB200_EINVAL, "secondary queue required");
+  if (dev->n == 0) return 0;
+  if (dev->n > 0x7fffffff) return Fail(G4HB200_EINVAL, "batch too large (track indices are 32 bit)");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  StageTimer t{h, st};
+  G4H_CUDA(t.Begin(dev->n));
+  const int fullGrid = FusedGrid(h, GammaFusedStepKernel<kMode>, dev->n);
+  const int64_t perLaunch = static_cast<int64_t>(fullGrid) * kFusedMaxTilesPerCta * kThreadsPerBlock;
+  G4H_CUDA(t.Before(kSGammaFused));
+  for (int64_t lo = 0; lo < dev->n; lo += perLaunch) {
+    const int64_t len = dev->n - lo < perLaunch ? dev->n - lo : perLaunch;
+    G4HB200GammaBatch part = GammaBatchView(*dev, lo, len);
+    G4HB200SecondaryQueue q = *sec;
+    q.parent_base = sec->parent_base + static_cast<int32_t>(lo);
+    if (kMode == 2 && slab != nullptr) {
+      TrackGeo geo = slab->geo;
+      geo.posx_posy += 2 * lo;
+      geo.posz_pad += 2 * lo;
+      geo.vol += lo;
+      geo.nextVol += lo;
+      ShowerGammaFusedKernel<<<FusedGrid(h, ShowerGammaFusedKernel, len), kThreadsPerBlock, 0, st>>>(h->view, part, q, seed, slab->g, geo);
+    } else {
+      GammaFusedStepKernel<kMode><<<FusedGrid(h, GammaFusedStepKernel<kMode>, len), kThreadsPerBlock, 0, st>>>(h->view, part, q, seed);
+    }
+    ++h->launches;
+  }
+  --h->launches;
+  G4H_CUDA(t.After(kSGammaFused));
+  if (t.tc != nullptr) G4H_CUDA(cudaEventRecord(t.tc->done, st));
+  G4H_CUDA(cudaGetLastError());
+  return 0;
+}
+
 // A sub-range of a batch (same struct, pointers advanced).
 G4HB200ElectronBatch ElectronBatchView(const G4HB200ElectronBatch& full, int64_t lo, int64_t len) {
   G4HB200ElectronBatch v = full;
-  double** g[16];
+  double** g[kNumElGroups];
   ElectronDoubleGroups(&v, g);
-  for (int k = 0; k < 16; ++k) if (*g[k] != nullptr) *g[k] += 2 * lo;
+  for (int k = 0; k < kNumElGroups; ++k) if (*g[k] != nullptr) *g[k] += 2 * lo;
   if (v.meta != nullptr) v.meta += 4 * lo;
   if (v.winner != nullptr) v.winner += lo;
   v.n = len;
@@ -662,6 +771,24 @@ int LaunchGammaPipelineHalves(G4HB200* h, G4HB200GammaBatch* dev, G4HB200Seconda
 
 }  // namespace
 
+namespace {
+template <int kOp>
+int LaunchElectronTrackOp(G4HB200* h, G4HB200ElectronBatch* dev, const G4HB200SecondaryQueue& q, uint64_t seed, int32_t* flag,
+                          cudaStream_t st) {
+  ElTrackOpKernel<kOp><<<OneWave(h, ElTrackOpKernel<kOp>, dev->n), kThreadsPerBlock, 0, st>>>(h->view, *dev, q, seed, flag);
+  ++h->launches;
+  G4H_CUDA(cudaGetLastError());
+  return 0;
+}
+template <int kOp>
+int LaunchGammaTrackOp(G4HB200* h, G4HB200GammaBatch* dev, const G4HB200SecondaryQueue& q, uint64_t seed, cudaStream_t st) {
+  GammaTrackOpKernel<kOp><<<OneWave(h, GammaTrackOpKernel<kOp>, dev->n), kThreadsPerBlock, 0, st>>>(h->view, *dev, q, seed);
+  ++h->launches;
+  G4H_CUDA(cudaGetLastError());
+  return 0;
+}
+}  // namespace
+
 extern "C" {
 
 const char* g4hb200_last_error(void) { return g_lastError.c_str(); }
@@ -754,6 +881,7 @@ int g4hb200_create(const G4HB200Tables* tables, int device, G4HB200** out) {
   {
     const char* mono = std::getenv("G4HB200_MONOLITH");
     h->monolith = mono != nullptr && mono[0] == '1';
+    if (const char* fu = std::getenv("G4HB200_FUSED")) h->fused = fu[0] != '0';
     if (const char* sp = std::getenv("G4HB200_SPLIT_MIN")) h->splitThreshold = std::atoll(sp);
     if (const char* sp = std::getenv("G4HB200_SPLIT_PARTS")) {
       const int v = std::atoi(sp);
@@ -805,9 +933,9 @@ int g4hb200_electron_batch_alloc(G4HB200* h, int64_t capacity, G4HB200ElectronBa
   if (rc != 0) return rc;
   if (out == nullptr || capacity < 0) return Fail(G4HB200_EINVAL, "bad argument");
   std::memset(out, 0, sizeof(*out));
-  double** g[16];
+  double** g[kNumElGroups];
   ElectronDoubleGroups(out, g);
-  for (int i = 0; i < 16; ++i) {
+  for (int i = 0; i < kNumElGroups; ++i) {
     rc = DevAlloc(*g[i], static_cast<size_t>(capacity) * 2);
     if (rc != 0) return rc;
   }
@@ -823,9 +951,9 @@ int g4hb200_electron_batch_free(G4HB200* h, G4HB200ElectronBatch* dev) {
   int rc = CheckHandle(h);
   if (rc != 0) return rc;
   if (dev == nullptr) return 0;
-  double** g[16];
+  double** g[kNumElGroups];
   ElectronDoubleGroups(dev, g);
-  for (int i = 0; i < 16; ++i) cudaFree(*g[i]);
+  for (int i = 0; i < kNumElGroups; ++i) cudaFree(*g[i]);
   cudaFree(dev->meta);
   cudaFree(dev->winner);
   std::memset(dev, 0, sizeof(*dev));
@@ -904,14 +1032,14 @@ int g4hb200_electron_batch_upload(G4HB200* h, const G4HB200ElectronBatch* host, 
   int rc = CheckHandle(h);
   if (rc != 0) return rc;
   if (host == nullptr || dev == nullptr) return Fail(G4HB200_EINVAL, "null batch");
-  return CopyElectron(host, dev, cudaMemcpyHostToDevice, static_cast<cudaStream_t>(stream), 0, 16, true, true);
+  return CopyElectron(host, dev, cudaMemcpyHostToDevice, static_cast<cudaStream_t>(stream), 0, kNumElGroups, true, true);
 }
 
 int g4hb200_electron_batch_download(G4HB200* h, const G4HB200ElectronBatch* dev, G4HB200ElectronBatch* host, void* stream) {
   int rc = CheckHandle(h);
   if (rc != 0) return rc;
   if (host == nullptr || dev == nullptr) return Fail(G4HB200_EINVAL, "null batch");
-  return CopyElectron(dev, host, cudaMemcpyDeviceToHost, static_cast<cudaStream_t>(stream), 0, 16, true, true);
+  return CopyElectron(dev, host, cudaMemcpyDeviceToHost, static_cast<cudaStream_t>(stream), 0, kNumElGroups, true, true);
 }
 
 int g4hb200_gamma_batch_upload(G4HB200* h, const G4HB200GammaBatch* host, G4HB200GammaBatch* dev, void* stream) {
@@ -952,6 +1080,31 @@ int g4hb200_sync(G4HB200* h, void* stream) {
   int rc = CheckHandle(h);
   if (rc != 0) return rc;
   G4H_CUDA(cudaStreamSynchronize(static_cast<cudaStream_t>(stream)));
+  return 0;
+}
+
+int g4hb200_device_alloc(G4HB200* h, size_t bytes, void** out) {
+  int rc = CheckHandle(h);
+  if (rc != 0) return rc;
+  if (out == nullptr) return Fail(G4HB200_EINVAL, "null argument");
+  const cudaError_t err = cudaMalloc(out, bytes > 0 ? bytes : 16);
+  if (err != cudaSuccess) return Fail(err == cudaErrorMemoryAllocation ? G4HB200_ENOMEM : G4HB200_ECUDA, "cudaMalloc", err);
+  return 0;
+}
+
+int g4hb200_device_free(G4HB200* h, void* p) {
+  int rc = CheckHandle(h);
+  if (rc != 0) return rc;
+  if (p != nullptr) G4H_CUDA(cudaFree(p));
+  return 0;
+}
+
+int g4hb200_memcpy(G4HB200* h, void* dst, const void* src, size_t bytes, int to_device, void* stream) {
+  int rc = CheckHandle(h);
+  if (rc != 0) return rc;
+  if (bytes == 0) return 0;
+  if (dst == nullptr || src == nullptr) return Fail(G4HB200_EINVAL, "null argument");
+  G4H_CUDA(cudaMemcpyAsync(dst, src, bytes, to_device ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToHost, static_cast<cudaStream_t>(stream)));
   return 0;
 }
 
@@ -1074,10 +1227,12 @@ int g4hb200_electron_howfar(G4HB200* h, G4HB200ElectronBatch* dev, uint64_t seed
 }
 int g4hb200_electron_perform(G4HB200* h, G4HB200ElectronBatch* dev, G4HB200SecondaryQueue* sec, uint64_t seed, void* stream) {
   if (h != nullptr && h->monolith) return LaunchElectron<1>(h, dev, sec, seed, stream);
+  if (h != nullptr && h->fused) return LaunchElectronFused<true>(h, dev, sec, seed, stream);
   return LaunchElectronPipelineHalves<false>(h, dev, sec, seed, stream);
 }
 int g4hb200_electron_step(G4HB200* h, G4HB200ElectronBatch* dev, G4HB200SecondaryQueue* sec, uint64_t seed, void* stream) {
   if (h != nullptr && h->monolith) return LaunchElectron<2>(h, dev, sec, seed, stream);
+  if (h != nullptr && h->fused) return LaunchElectronFused<false>(h, dev, sec, seed, stream);
   return LaunchElectronPipelineHalves<true>(h, dev, sec, seed, stream);
 }
 int g4hb200_gamma_howfar(G4HB200* h, G4HB200GammaBatch* dev, uint64_t seed, void* stream) {
@@ -1085,11 +1240,72 @@ int g4hb200_gamma_howfar(G4HB200* h, G4HB200GammaBatch* dev, uint64_t seed, void
 }
 int g4hb200_gamma_perform(G4HB200* h, G4HB200GammaBatch* dev, G4HB200SecondaryQueue* sec, uint64_t seed, void* stream) {
   if (h != nullptr && h->monolith) return LaunchGamma<1>(h, dev, sec, seed, stream);
+  if (h != nullptr && h->fused) return LaunchGammaFused<1>(h, dev, sec, seed, stream);
   return LaunchGammaPipelineHalves<1>(h, dev, sec, seed, stream);
 }
 int g4hb200_gamma_step(G4HB200* h, G4HB200GammaBatch* dev, G4HB200SecondaryQueue* sec, uint64_t seed, void* stream) {
   if (h != nullptr && h->monolith) return LaunchGamma<2>(h, dev, sec, seed, stream);
+  if (h != nullptr && h->fused) return LaunchGammaFused<2>(h, dev, sec, seed, stream);
   return LaunchGammaPipelineHalves<2>(h, dev, sec, seed, stream);
+}
+
+
+int g4hb200_electron_track_op(G4HB200* h, int op, G4HB200ElectronBatch* dev, G4HB200SecondaryQueue* sec, uint64_t seed,
+                              int32_t* out_flag, void* stream) {
+  int rc = CheckHandle(h);
+  if (rc != 0) return rc;
+  if (dev == nullptr || dev->n < 0) return Fail(G4HB200_EINVAL, "bad electron batch");
+  if (op < 0 || op >= kNumElTrackOps) return Fail(G4HB200_EINVAL, "unknown track-level op");
+  if ((op == kOpDiscrete || op == kOpAnnihilateAtRest) && sec == nullptr) return Fail(G4HB200_EINVAL, "secondary queue required");
+  if (dev->mfp01 == nullptr || dev->mfp23 == nullptr || dev->range_lambtr1 == nullptr || dev->tstep_zpath == nullptr ||
+      dev->par12 == nullptr || dev->par3_pad == nullptr)
+    return Fail(G4HB200_EINVAL, "the track-level calls need the hand-over groups of the batch");
+  if (dev->n == 0) return 0;
+  const G4HB200SecondaryQueue q = sec != nullptr ? *sec : NullQueue();
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  switch (op) {
+    case kOpHowFarDiscrete: return LaunchElectronTrackOp<kOpHowFarDiscrete>(h, dev, q, seed, out_flag, st);
+    case kOpHowFarMSC: return LaunchElectronTrackOp<kOpHowFarMSC>(h, dev, q, seed, out_flag, st);
+    case kOpUpdatePStep: return LaunchElectronTrackOp<kOpUpdatePStep>(h, dev, q, seed, out_flag, st);
+    case kOpUpdateNIA: return LaunchElectronTrackOp<kOpUpdateNIA>(h, dev, q, seed, out_flag, st);
+    case kOpMeanELoss: return LaunchElectronTrackOp<kOpMeanELoss>(h, dev, q, seed, out_flag, st);
+    case kOpSampleMSC: return LaunchElectronTrackOp<kOpSampleMSC>(h, dev, q, seed, out_flag, st);
+    case kOpLossFluct: return LaunchElectronTrackOp<kOpLossFluct>(h, dev, q, seed, out_flag, st);
+    case kOpDiscrete: return LaunchElectronTrackOp<kOpDiscrete>(h, dev, q, seed, out_flag, st);
+    case kOpAnnihilateAtRest: return LaunchElectronTrackOp<kOpAnnihilateAtRest>(h, dev, q, seed, out_flag, st);
+    case kOpPerformContinuous: return LaunchElectronTrackOp<kOpPerformContinuous>(h, dev, q, seed, out_flag, st);
+    default: return LaunchElectronTrackOp<kOpResampleNIA>(h, dev, q, seed, out_flag, st);
+  }
+}
+
+int g4hb200_electron_check_delta(G4HB200* h, G4HB200ElectronBatch* dev, const double* urnd, int32_t* out_flag, void* stream) {
+  int rc = CheckHandle(h);
+  if (rc != 0) return rc;
+  if (dev == nullptr || dev->n < 0 || dev->mfp01 == nullptr || dev->mfp23 == nullptr) return Fail(G4HB200_EINVAL, "bad electron batch");
+  if (dev->n > 0 && (urnd == nullptr || out_flag == nullptr)) return Fail(G4HB200_EINVAL, "null argument");
+  if (dev->n == 0) return 0;
+  ElCheckDeltaKernel<<<OneWave(h, ElCheckDeltaKernel, dev->n), kThreadsPerBlock, 0, static_cast<cudaStream_t>(stream)>>>(h->view, *dev, urnd,
+                                                                                                                         out_flag);
+  ++h->launches;
+  G4H_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int g4hb200_gamma_track_op(G4HB200* h, int op, G4HB200GammaBatch* dev, G4HB200SecondaryQueue* sec, uint64_t seed, void* stream) {
+  int rc = CheckHandle(h);
+  if (rc != 0) return rc;
+  if (dev == nullptr || dev->n < 0) return Fail(G4HB200_EINVAL, "bad gamma batch");
+  if (op < 0 || op >= kNumGmTrackOps) return Fail(G4HB200_EINVAL, "unknown track-level op");
+  if (op == kGOpPerformSelected && sec == nullptr) return Fail(G4HB200_EINVAL, "secondary queue required");
+  if (dev->n == 0) return 0;
+  const G4HB200SecondaryQueue q = sec != nullptr ? *sec : NullQueue();
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  switch (op) {
+    case kGOpHowFarTrack: return LaunchGammaTrackOp<kGOpHowFarTrack>(h, dev, q, seed, st);
+    case kGOpUpdateNIA: return LaunchGammaTrackOp<kGOpUpdateNIA>(h, dev, q, seed, st);
+    case kGOpSelectInteraction: return LaunchGammaTrackOp<kGOpSelectInteraction>(h, dev, q, seed, st);
+    default: return LaunchGammaTrackOp<kGOpPerformSelected>(h, dev, q, seed, st);
+  }
 }
 
 // Host buffers in, host buffers out.  The batch is cut into chunks that travel on kNumSlots streams: while chunk c
@@ -1102,8 +1318,12 @@ int g4hb200_electron_step_host(G4HB200* h, G4HB200ElectronBatch* host, G4HB200Se
   if (host == nullptr || hostSec == nullptr) return Fail(G4HB200_EINVAL, "null argument");
   const int64_t n = host->n;
   if (n < 0 || n > 0x3fffffff) return Fail(G4HB200_EINVAL, "bad batch size");
+  if (hostSec->count == nullptr) return Fail(G4HB200_EINVAL, "secondary queue without a counter");
   hostSec->count[0] = 0;
   if (n == 0) return 0;
+  // a step creates at most two secondaries per track: checked BEFORE anything is uploaded or launched, so that a queue
+  // that is too small never costs the caller the step (the primaries would already have lost their energy)
+  if (hostSec->capacity < 2 * n) return Fail(G4HB200_ECAPACITY, "host secondary queue must hold 2 records per track");
   if (n > h->elCap) {
     if (h->elCap > 0) g4hb200_electron_batch_free(h, &h->elDev);
     h->elCap = 0;
@@ -1157,7 +1377,9 @@ int g4hb200_electron_step_host(G4HB200* h, G4HB200ElectronBatch* host, G4HB200Se
     q.parent_base = static_cast<int32_t>(lo);
     // H2D: the 7 persistent groups + meta (128 B / track)
     if ((rc = CopyElectron(&hv, &dv, cudaMemcpyHostToDevice, slot.stream, 0, 7, true, false)) != 0) return rc;
-    if ((rc = LaunchElectronPipeline<true>(h, &dv, &q, seed, slot.stream, c % G4HB200::kNumSlots)) != 0) return rc;
+    if ((rc = h->fused ? LaunchElectronFused<false>(h, &dv, &q, seed, slot.stream, nullptr, c % G4HB200::kNumSlots)
+                       : LaunchElectronPipeline<true>(h, &dv, &q, seed, slot.stream, c % G4HB200::kNumSlots)) != 0)
+      return rc;
     // D2H: persistent + result groups + meta + winner (180 B / track)
     if ((rc = CopyElectron(&dv, &hv, cudaMemcpyDeviceToHost, slot.stream, 0, 10, true, true)) != 0) return rc;
     G4H_CUDA(cudaMemcpyAsync(h->pinnedCounts + c, h->chunkCounters + c, sizeof(int32_t), cudaMemcpyDeviceToHost, slot.stream));
@@ -1196,22 +1418,28 @@ int g4hb200_gamma_step_host(G4HB200* h, G4HB200GammaBatch* host, G4HB200Secondar
   if (rc != 0) return rc;
   if (host == nullptr || hostSec == nullptr) return Fail(G4HB200_EINVAL, "null argument");
   const int64_t n = host->n;
+  if (n < 0 || n > 0x3fffffff) return Fail(G4HB200_EINVAL, "bad batch size");
+  if (hostSec->count == nullptr) return Fail(G4HB200_EINVAL, "secondary queue without a counter");
+  hostSec->count[0] = 0;
+  if (n == 0) return 0;
+  if (hostSec->capacity < 2 * n) return Fail(G4HB200_ECAPACITY, "host secondary queue must hold 2 records per track");
   if (n > h->gmCap) {
     if (h->gmCap > 0) g4hb200_gamma_batch_free(h, &h->gmDev);
     h->gmCap = 0;
     if ((rc = g4hb200_gamma_batch_alloc(h, n, &h->gmDev)) != 0) return rc;
     h->gmCap = n;
   }
-  if (hostSec->capacity > h->secCap) {
+  if (2 * n > h->secCap) {
     if (h->secCap > 0) g4hb200_secondary_queue_free(h, &h->secDev);
     h->secCap = 0;
-    if ((rc = g4hb200_secondary_queue_alloc(h, hostSec->capacity, &h->secDev)) != 0) return rc;
-    h->secCap = hostSec->capacity;
+    if ((rc = g4hb200_secondary_queue_alloc(h, 2 * n, &h->secDev)) != 0) return rc;
+    h->secCap = 2 * n;
   }
   cudaStream_t st = h->stream;
   if ((rc = CopyGamma(host, &h->gmDev, cudaMemcpyHostToDevice, st, 0, 3, true, false)) != 0) return rc;
   if ((rc = g4hb200_secondary_queue_reset(h, &h->secDev, st)) != 0) return rc;
-  if ((rc = LaunchGammaPipeline<2>(h, &h->gmDev, &h->secDev, seed, st)) != 0) return rc;
+  if ((rc = h->fused ? LaunchGammaFused<2>(h, &h->gmDev, &h->secDev, seed, st) : LaunchGammaPipeline<2>(h, &h->gmDev, &h->secDev, seed, st)) != 0)
+    return rc;
   if ((rc = CopyGamma(&h->gmDev, host, cudaMemcpyDeviceToHost, st, 0, 5, true, true)) != 0) return rc;
   if ((rc = g4hb200_secondary_queue_download(h, &h->secDev, hostSec, st)) != 0) return rc;
   G4H_CUDA(cudaStreamSynchronize(st));

@@ -217,7 +217,9 @@ int RunStepLoop(G4HB200* h, const G4HB200SlabGeometry* geom, int64_t numPrimarie
         // HowFar + geometry step + Perform: the head of the pipeline does the first two and the along-step part of
         // the third in one pass (ShowerElectronHeadKernel), the queue kernels of Perform follow
         const SlabHead slab{g, s.elGeo[cur]};
-        if ((status = LaunchElectronPipelineHalves<true>(h, &b, &s.secEl, seed, st, &slab)) != 0) break;
+        if ((status = h->fused ? LaunchElectronFused<false>(h, &b, &s.secEl, seed, st, &slab)
+                               : LaunchElectronPipelineHalves<true>(h, &b, &s.secEl, seed, st, &slab)) != 0)
+          break;
       }
       ShowerElectronPostKernel<<<OneWave(h, ShowerElectronPostKernel, nEl), kThreadsPerBlock, 0, st>>>(
           g, b, s.elGeo[cur], s.el[nxt], s.elGeo[nxt], s.score);
@@ -239,7 +241,9 @@ int RunStepLoop(G4HB200* h, const G4HB200SlabGeometry* geom, int64_t numPrimarie
       } else {
         // HowFar + geometry step + SelectInteraction / Perform: one head kernel (ShowerGammaHeadKernel), then the samplers
         const SlabHead slab{g, s.gmGeo[cur]};
-        if ((status = LaunchGammaPipelineHalves<2>(h, &b, &s.secGm, seed, sg, &slab)) != 0) break;
+        if ((status = h->fused ? LaunchGammaFused<2>(h, &b, &s.secGm, seed, sg, &slab)
+                               : LaunchGammaPipelineHalves<2>(h, &b, &s.secGm, seed, sg, &slab)) != 0)
+          break;
       }
       ShowerGammaPostKernel<<<OneWave(h, ShowerGammaPostKernel, nGm), kThreadsPerBlock, 0, sg>>>(
           g, b, s.gmGeo[cur], s.gm[nxt], s.gmGeo[nxt], s.score);

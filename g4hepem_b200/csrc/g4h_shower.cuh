@@ -24,6 +24,7 @@
 
 #include "g4h_kernels.cuh"
 #include "g4h_pipeline.cuh"
+#include "g4h_fused.cuh"
 
 namespace g4h {
 
@@ -306,6 +307,33 @@ ShowerElectronHeadKernel(const __grid_constant__ TablesView tv, const __grid_con
     const int route = i < b.n ? StageStepHead(tv, b, w.prestep, i, seed, geometry) : -1;
     RouteToQueues<5>(cc, route, static_cast<int32_t>(i), w.queue, w.count);
   }
+}
+
+// ---- the loop's steps as single persistent launches (g4h_fused.cuh) with the geometry step inside the head -------------
+struct MakeSlabGeometry {
+  const SlabGeom& g;
+  const TrackGeo& geo;
+  const double* dirx_diry;
+  __device__ __forceinline__ SlabGeometryStep operator()() const { return SlabGeometryStep{g, geo, dirx_diry}; }
+};
+struct MakeSlabGammaGeometry {
+  const SlabGeom& g;
+  const TrackGeo& geo;
+  __device__ __forceinline__ SlabGammaGeometryStep operator()() const { return SlabGammaGeometryStep{g, geo}; }
+};
+
+__global__ void __launch_bounds__(kThreadsPerBlock, G4H_MINB_FUSED)
+ShowerElectronFusedKernel(const __grid_constant__ TablesView tv, const __grid_constant__ G4HB200ElectronBatch b, double* prestep,
+                          const __grid_constant__ G4HB200SecondaryQueue sq, uint64_t seed, const __grid_constant__ SlabGeom g,
+                          const __grid_constant__ TrackGeo geo) {
+  ElFusedBody<false>(tv, b, prestep, sq, seed, MakeSlabGeometry{g, geo, b.dirx_diry});
+}
+
+__global__ void __launch_bounds__(kThreadsPerBlock, G4H_MINB_FUSED)
+ShowerGammaFusedKernel(const __grid_constant__ TablesView tv, const __grid_constant__ G4HB200GammaBatch b,
+                       const __grid_constant__ G4HB200SecondaryQueue sq, uint64_t seed, const __grid_constant__ SlabGeom g,
+                       const __grid_constant__ TrackGeo geo) {
+  GammaFusedBody<2>(tv, b, sq, seed, MakeSlabGammaGeometry{g, geo});
 }
 
 // ---- geometry step: between HowFar and Perform ------------------------------------------------------------------

@@ -252,6 +252,66 @@ class ElectronManager:
                     "electron_step")
 
 
+    # ---- the track-level statics the production caller drives one by one (G4HepEmElectronManager.hh:90-206) -------------
+    @staticmethod
+    def _op(engine, op, batch, secondaries=None, seed=0, flags=None, stream=None):
+        s = batch.as_struct()
+        q = secondaries.as_struct() if secondaries is not None else None
+        _capi.check(engine.lib.g4hb200_electron_track_op(engine.handle, op, C.byref(s), C.byref(q) if q is not None else None, seed,
+                                                         flags.data_ptr() if flags is not None else None, _stream_ptr(stream)),
+                    f"electron_track_op({op})")
+
+    @staticmethod
+    def ResampleNumIALeft(engine, batch, seed, stream=None):
+        ElectronManager._op(engine, _capi.OP_RESAMPLE_NIA, batch, seed=seed, stream=stream)
+
+    @staticmethod
+    def HowFarToDiscreteInteraction(engine, batch, stream=None):
+        ElectronManager._op(engine, _capi.OP_HOWFAR_DISCRETE, batch, stream=stream)
+
+    @staticmethod
+    def HowFarToMSC(engine, batch, seed, stream=None):
+        ElectronManager._op(engine, _capi.OP_HOWFAR_MSC, batch, seed=seed, stream=stream)
+
+    @staticmethod
+    def UpdatePStepLength(engine, batch, stream=None):
+        ElectronManager._op(engine, _capi.OP_UPDATE_PSTEP, batch, stream=stream)
+
+    @staticmethod
+    def UpdateNumIALeft(engine, batch, stream=None):
+        ElectronManager._op(engine, _capi.OP_UPDATE_NIA, batch, stream=stream)
+
+    @staticmethod
+    def ApplyMeanEnergyLoss(engine, batch, stopped=None, stream=None):
+        ElectronManager._op(engine, _capi.OP_MEAN_ELOSS, batch, flags=stopped, stream=stream)
+
+    @staticmethod
+    def SampleMSC(engine, batch, seed, stream=None):
+        ElectronManager._op(engine, _capi.OP_SAMPLE_MSC, batch, seed=seed, stream=stream)
+
+    @staticmethod
+    def SampleLossFluctuations(engine, batch, seed, stopped=None, stream=None):
+        ElectronManager._op(engine, _capi.OP_LOSS_FLUCT, batch, seed=seed, flags=stopped, stream=stream)
+
+    @staticmethod
+    def PerformContinuous(engine, batch, seed, stopped=None, stream=None):
+        ElectronManager._op(engine, _capi.OP_PERFORM_CONTINUOUS, batch, seed=seed, flags=stopped, stream=stream)
+
+    @staticmethod
+    def PerformDiscrete(engine, batch, secondaries, seed, stream=None):
+        ElectronManager._op(engine, _capi.OP_DISCRETE, batch, secondaries, seed, stream=stream)
+
+    @staticmethod
+    def AnnihilateAtRest(engine, batch, secondaries, seed, stream=None):
+        ElectronManager._op(engine, _capi.OP_ANNIHILATE_AT_REST, batch, secondaries, seed, stream=stream)
+
+    @staticmethod
+    def CheckDelta(engine, batch, urnd, flags, stream=None):
+        s = batch.as_struct()
+        _capi.check(engine.lib.g4hb200_electron_check_delta(engine.handle, C.byref(s), urnd.data_ptr(), flags.data_ptr(),
+                                                            _stream_ptr(stream)), "electron_check_delta")
+
+
 class GammaManager:
     """Batch counterpart of G4HepEmGammaManager (G4HepEmRun/include/G4HepEmGammaManager.hh:21-57)."""
 
@@ -274,3 +334,27 @@ class GammaManager:
         q = secondaries.as_struct()
         _capi.check(engine.lib.g4hb200_gamma_step(engine.handle, C.byref(s), C.byref(q), seed, _stream_ptr(stream)),
                     "gamma_step")
+
+    # ---- the track-level statics (G4HepEmGammaManager.hh:34-51) --------------------------------------------------------------
+    @staticmethod
+    def _op(engine, op, batch, secondaries=None, seed=0, stream=None):
+        s = batch.as_struct()
+        q = secondaries.as_struct() if secondaries is not None else None
+        _capi.check(engine.lib.g4hb200_gamma_track_op(engine.handle, op, C.byref(s), C.byref(q) if q is not None else None, seed,
+                                                      _stream_ptr(stream)), f"gamma_track_op({op})")
+
+    @staticmethod
+    def HowFarTrack(engine, batch, stream=None):
+        GammaManager._op(engine, _capi.GOP_HOWFAR_TRACK, batch, stream=stream)
+
+    @staticmethod
+    def UpdateNumIALeft(engine, batch, stream=None):
+        GammaManager._op(engine, _capi.GOP_UPDATE_NIA, batch, stream=stream)
+
+    @staticmethod
+    def SelectInteraction(engine, batch, seed, stream=None):
+        GammaManager._op(engine, _capi.GOP_SELECT_INTERACTION, batch, seed=seed, stream=stream)
+
+    @staticmethod
+    def PerformSelected(engine, batch, secondaries, seed, stream=None):
+        GammaManager._op(engine, _capi.GOP_PERFORM_SELECTED, batch, secondaries, seed, stream=stream)

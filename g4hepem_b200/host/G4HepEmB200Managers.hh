@@ -62,10 +62,16 @@ class G4HepEmB200Session {
     if (fElCap > 0) g4hb200_electron_batch_free(fHandle, &fElDev);
     if (fGmCap > 0) g4hb200_gamma_batch_free(fHandle, &fGmDev);
     if (fSecCap > 0) g4hb200_secondary_queue_free(fHandle, &fSecDev);
+    if (fFlagDev != nullptr) g4hb200_device_free(fHandle, fFlagDev);
     g4hb200_destroy(fHandle);
     fHandle = nullptr;
-    fElCap = fGmCap = fSecCap = 0;
+    fFlagDev = nullptr;
+    fElCap = fGmCap = fSecCap = fFlagCap = 0;
   }
+  bool IsOpen() const { return fHandle != nullptr; }
+  G4HB200* Handle() const { return fHandle; }
+  uint64_t Seed() const { return fSeed; }
+  void SetSeed(uint64_t seed) { fSeed = seed; }
   const char* LastError() const { return g4hb200_last_error(); }
 
   int ElectronHowFar(G4HepEmElectronTrack* tracks, G4HepEmB200TrackAux* aux, int64_t n) { return RunElectron(tracks, aux, n, 0, nullptr); }
@@ -85,9 +91,24 @@ class G4HepEmB200Session {
     return RunGamma(tracks, aux, n, 2, sec);
   }
 
+  // ---- the track-level statics of the managers, one at a time over an array of tracks (G4HB200_OP_* / G4HB200_GOP_* of
+  // include/g4hepem_b200.h; G4HepEmElectronManager.hh:90-206, G4HepEmGammaManager.hh:34-51).  flags[i] (may be null): the bool
+  // the reference's function returns.  sec (may be null): the secondaries of the ops that create some.
+  int ElectronTrackOp(int op, G4HepEmElectronTrack* tracks, G4HepEmB200TrackAux* aux, int64_t n, std::vector<G4HepEmB200Secondary>* sec,
+                      int32_t* flags) {
+    return RunElectron(tracks, aux, n, 3 + op, sec, flags);
+  }
+  int GammaTrackOp(int op, G4HepEmGammaTrack* tracks, G4HepEmB200TrackAux* aux, int64_t n, std::vector<G4HepEmB200Secondary>* sec) {
+    return RunGamma(tracks, aux, n, 3 + op, sec);
+  }
+  // CheckDelta(data, track, rand) (G4HepEmElectronManager.hh:195): isDelta[i] for uniform urnd[i]
+  int ElectronCheckDelta(G4HepEmElectronTrack* tracks, G4HepEmB200TrackAux* aux, int64_t n, const double* urnd, int32_t* isDelta) {
+    return RunElectron(tracks, aux, n, -1, nullptr, isDelta, urnd);
+  }
+
  private:
   struct HostElectron {
-    std::vector<double> g[16];
+    std::vector<double> g[17];
     std::vector<int32_t> meta, winner;
     G4HB200ElectronBatch view;
     void Resize(int64_t n) {
@@ -95,10 +116,10 @@ class G4HepEmB200Session {
       meta.assign(static_cast<size_t>(4 * n), 0);
       winner.assign(static_cast<size_t>(n), -1);
       view.n = n;
-      double** p[16] = {&view.ekin_logekin, &view.dirx_diry, &view.dirz_safety, &view.nia01, &view.nia23, &view.msc_irange_dynrf,
+      double** p[17] = {&view.ekin_logekin, &view.dirx_diry, &view.dirz_safety, &view.nia01, &view.nia23, &view.msc_irange_dynrf,
                         &view.msc_tlimmin_gauss, &view.gstep_pstep, &view.edep_dispx, &view.dispy_dispz, &view.mfp01, &view.mfp23,
-                        &view.range_lambtr1, &view.tstep_zpath, &view.par12, &view.par3_pad};
-      for (int k = 0; k < 16; ++k) *p[k] = g[k].data();
+                        &view.range_lambtr1, &view.tstep_zpath, &view.par12, &view.par3_pad, &view.prestep};
+      for (int k = 0; k < 17; ++k) *p[k] = g[k].data();
       view.meta = meta.data();
       view.winner = winner.data();
     }
@@ -191,6 +212,8 @@ class G4HepEmB200Session {
     b.par12[2 * i]             = msc->fPar1;
     b.par12[2 * i + 1]         = msc->fPar2;
     b.par3_pad[2 * i]          = msc->fPar3;
+    b.prestep[2 * i]           = et.GetPreStepEKin();
+    b.prestep[2 * i + 1]       = et.GetPreStepLogEKin();
   }
 
   // row i -> G4HepEmElectronTrack (in place, like the reference's managers)
@@ -231,6 +254,7 @@ class G4HepEmB200Session {
     msc->fPar1           = b.par12[2 * i];
     msc->fPar2           = b.par12[2 * i + 1];
     msc->fPar3           = b.par3_pad[2 * i];
+    et.SetPreStepEKin(b.prestep[2 * i], b.prestep[2 * i + 1]);
   }
 
   static void Pack(G4HepEmGammaTrack& gt, const G4HepEmB200TrackAux& a, G4HB200GammaBatch& b, int64_t i) {
@@ -304,11 +328,30 @@ class G4HepEmB200Session {
     return 0;
   }
 
-  // mode 0: HowFar, 1: Perform, 2: fused step
-  int RunElectron(G4HepEmElectronTrack* tracks, G4HepEmB200TrackAux* aux, int64_t n, int mode, std::vector<G4HepEmB200Secondary>* sec) {
+  int EnsureFlags(int64_t n) {
+    if (n <= fFlagCap) return 0;
+    if (fFlagDev != nullptr) g4hb200_device_free(fHandle, fFlagDev);
+    fFlagDev = nullptr;
+    fFlagCap = 0;
+    void* p = nullptr;
+    const int rc = g4hb200_device_alloc(fHandle, static_cast<size_t>(n) * 16, &p);
+    if (rc != 0) return rc;
+    fFlagDev = p;
+    fFlagCap = n;
+    return 0;
+  }
+
+  // mode 0: HowFar, 1: Perform, 2: fused step, 3 + op: one track-level op, -1: CheckDelta with the uniforms urnd
+  int RunElectron(G4HepEmElectronTrack* tracks, G4HepEmB200TrackAux* aux, int64_t n, int mode, std::vector<G4HepEmB200Secondary>* sec,
+                  int32_t* flags = nullptr, const double* urnd = nullptr) {
     if (fHandle == nullptr) return G4HB200_EINVAL;
     if (n <= 0) return 0;
     int rc = 0;
+    if (mode >= 3 || mode < 0) {
+      if ((rc = EnsureFlags(n)) != 0) return rc;
+    }
+    int32_t* flagDev = static_cast<int32_t*>(fFlagDev);
+    double* urndDev  = reinterpret_cast<double*>(static_cast<char*>(fFlagDev) + 8 * (fFlagCap > 0 ? fFlagCap : 0));
     if (n > fElCap) {
       if (fElCap > 0) g4hb200_electron_batch_free(fHandle, &fElDev);
       fElCap = 0;
@@ -322,8 +365,16 @@ class G4HepEmB200Session {
     if (mode == 0) rc = g4hb200_electron_howfar(fHandle, &fElDev, fSeed, nullptr);
     if (mode == 1) rc = g4hb200_electron_perform(fHandle, &fElDev, &fSecDev, fSeed, nullptr);
     if (mode == 2) rc = g4hb200_electron_step(fHandle, &fElDev, &fSecDev, fSeed, nullptr);
+    if (mode >= 3) rc = g4hb200_electron_track_op(fHandle, mode - 3, &fElDev, &fSecDev, fSeed, flagDev, nullptr);
+    if (mode < 0) {
+      if ((rc = g4hb200_memcpy(fHandle, urndDev, urnd, static_cast<size_t>(n) * 8, 1, nullptr)) != 0) return rc;
+      rc = g4hb200_electron_check_delta(fHandle, &fElDev, urndDev, flagDev, nullptr);
+    }
     if (rc != 0) return rc;
     if ((rc = g4hb200_electron_batch_download(fHandle, &fElDev, &fElHost.view, nullptr)) != 0) return rc;
+    if (flags != nullptr && (mode >= 3 || mode < 0)) {
+      if ((rc = g4hb200_memcpy(fHandle, flags, flagDev, static_cast<size_t>(n) * 4, 0, nullptr)) != 0) return rc;
+    }
     if ((rc = g4hb200_sync(fHandle, nullptr)) != 0) return rc;
     for (int64_t i = 0; i < n; ++i) Unpack(fElHost.view, i, tracks[i], aux[i]);
     return mode != 0 ? FetchSecondaries(sec) : 0;
@@ -346,6 +397,7 @@ class G4HepEmB200Session {
     if (mode == 0) rc = g4hb200_gamma_howfar(fHandle, &fGmDev, fSeed, nullptr);
     if (mode == 1) rc = g4hb200_gamma_perform(fHandle, &fGmDev, &fSecDev, fSeed, nullptr);
     if (mode == 2) rc = g4hb200_gamma_step(fHandle, &fGmDev, &fSecDev, fSeed, nullptr);
+    if (mode >= 3) rc = g4hb200_gamma_track_op(fHandle, mode - 3, &fGmDev, &fSecDev, fSeed, nullptr);
     if (rc != 0) return rc;
     if ((rc = g4hb200_gamma_batch_download(fHandle, &fGmDev, &fGmHost.view, nullptr)) != 0) return rc;
     if ((rc = g4hb200_sync(fHandle, nullptr)) != 0) return rc;
@@ -359,7 +411,8 @@ class G4HepEmB200Session {
   G4HB200ElectronBatch fElDev;
   G4HB200GammaBatch fGmDev;
   G4HB200SecondaryQueue fSecDev;
-  int64_t fElCap = 0, fGmCap = 0, fSecCap = 0;
+  int64_t fElCap = 0, fGmCap = 0, fSecCap = 0, fFlagCap = 0;
+  void* fFlagDev = nullptr;  // device scratch of the track-level calls: int32 flags [cap] + padding, then uniforms [cap]
   HostElectron fElHost;
   HostGamma fGmHost;
   HostSecondaries fSecHost;

@@ -15,6 +15,7 @@
 #ifndef G4HEPEM_B200_H
 #define G4HEPEM_B200_H
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -166,6 +167,10 @@ typedef struct G4HB200ElectronBatch {
   double* tstep_zpath;     /* MSC fTrueStepLength, fZPathLength */
   double* par12;           /* MSC fPar1, fPar2 */
   double* par3_pad;        /* MSC fPar3, unused */
+  /* G4HepEmElectronTrack::fPreStepEKin, fPreStepLogEKin (G4HepEmElectronTrack.hh:57-72): state between the track-level
+   * calls only (g4hb200_electron_track_op); may be NULL for the HowFar / Perform / step entry points, which keep
+   * the pre-step energy in their own workspace */
+  double* prestep;
 } G4HB200ElectronBatch;
 
 /* gamma state: G4HepEmGammaTrack (G4HepEmRun/include/G4HepEmGammaTrack.hh:17-46) */
@@ -219,6 +224,11 @@ int g4hb200_gamma_batch_upload(G4HB200* h, const G4HB200GammaBatch* host, G4HB20
 int g4hb200_gamma_batch_download(G4HB200* h, const G4HB200GammaBatch* dev, G4HB200GammaBatch* host, void* stream);
 int g4hb200_secondary_queue_download(G4HB200* h, const G4HB200SecondaryQueue* dev, G4HB200SecondaryQueue* host, void* stream);
 int g4hb200_sync(G4HB200* h, void* stream);
+/* plain device scratch for the callers of the track-level entry points (flag / uniform arrays): no CUDA header needed on
+ * the host side.  to_device: 1 = host -> device, 0 = device -> host; asynchronous on `stream` */
+int g4hb200_device_alloc(G4HB200* h, size_t bytes, void** out);
+int g4hb200_device_free(G4HB200* h, void* p);
+int g4hb200_memcpy(G4HB200* h, void* dst, const void* src, size_t bytes, int to_device, void* stream);
 
 /* ---- table look-ups (BASELINE config 1) ---------------------------------------------------
  * One launch evaluates, per track, G4HepEmElectronManager::GetRestRange, GetRestDEDX,
@@ -275,6 +285,37 @@ int g4hb200_gamma_howfar(G4HB200* h, G4HB200GammaBatch* dev, uint64_t seed, void
  * callers do: G4HepEmTrackingManager.cc:1092-1108) followed by Perform (.icc:54-94). */
 int g4hb200_gamma_perform(G4HB200* h, G4HB200GammaBatch* dev, G4HB200SecondaryQueue* sec, uint64_t seed, void* stream);
 int g4hb200_gamma_step(G4HB200* h, G4HB200GammaBatch* dev, G4HB200SecondaryQueue* sec, uint64_t seed, void* stream);
+
+/* ---- track-level entry points: the pieces of a step, one launch each -------------------------------------------------
+ * The production caller of the reference does not use the two-call protocol: G4HepEmTrackingManager::TrackElectron
+ * (G4HepEm/G4HepEm/src/G4HepEmTrackingManager.cc:428-665) calls the static pieces of G4HepEmElectronManager
+ * (G4HepEmRun/include/G4HepEmElectronManager.hh:90-206) one by one with the geometry step and the MSC sub-step loop in
+ * between, TrackGamma (.cc:985-1140) those of G4HepEmGammaManager (G4HepEmGammaManager.hh:32-55).  One call applies
+ * ONE of them, in place, to every track of the device batch -- all groups of the batch, `prestep` included, are the
+ * state between calls (what the reference keeps in the G4HepEmElectronTrack / G4HepEmGammaTrack object).
+ * out_flag (device, int32[n], may be NULL): the bool the reference's function returns, for the ops that return one. */
+#define G4HB200_OP_HOWFAR_DISCRETE 0    /* HowFarToDiscreteInteraction(data, pars, elTrack)          .hh:90   .icc:48-101  */
+#define G4HB200_OP_HOWFAR_MSC 1         /* HowFarToMSC(data, pars, elTrack, rng)                     .hh:108  .icc:103-164 */
+#define G4HB200_OP_UPDATE_PSTEP 2       /* UpdatePStepLength(elTrack)                                .hh:133  .icc:171-203 */
+#define G4HB200_OP_UPDATE_NIA 3         /* UpdateNumIALeft(elTrack)                                  .hh:140  .icc:205-214 */
+#define G4HB200_OP_MEAN_ELOSS 4         /* ApplyMeanEnergyLoss(data, pars, elTrack) -> stopped       .hh:149  .icc:216-259 */
+#define G4HB200_OP_SAMPLE_MSC 5         /* SampleMSC(data, pars, elTrack, rng)                       .hh:158  .icc:261-322 */
+#define G4HB200_OP_LOSS_FLUCT 6         /* SampleLossFluctuations(data, pars, elTrack, rng) -> stopped .hh:167 .icc:324-368 */
+#define G4HB200_OP_DISCRETE 7           /* PerformDiscrete(data, pars, tlData)                       .hh:206  .icc:425-459 */
+#define G4HB200_OP_ANNIHILATE_AT_REST 8 /* G4HepEmPositronInteractionAnnihilation::Perform(tlData, true)  (...Annihilation.icc:15-50) */
+#define G4HB200_OP_PERFORM_CONTINUOUS 9 /* PerformContinuous(data, pars, elTrack, rng) -> stopped    .hh:184  .icc:375-405 */
+#define G4HB200_OP_RESAMPLE_NIA 10      /* fNumIALeft[ip] = -log(u) where <= 0: the loop of HowFar (.icc:39-43) and of
+                                           TrackElectron (G4HepEmTrackingManager.cc:430-434) */
+/* sec: required for the ops that create secondaries (DISCRETE, ANNIHILATE_AT_REST), may be NULL otherwise */
+int g4hb200_electron_track_op(G4HB200* h, int op, G4HB200ElectronBatch* dev, G4HB200SecondaryQueue* sec, uint64_t seed,
+                              int32_t* out_flag, void* stream);
+/* CheckDelta(data, track, rand) with caller supplied uniforms (.hh:195, .icc:408-423): out_flag[i] = 1 for a delta interaction */
+int g4hb200_electron_check_delta(G4HB200* h, G4HB200ElectronBatch* dev, const double* urnd, int32_t* out_flag, void* stream);
+#define G4HB200_GOP_HOWFAR_TRACK 0       /* HowFar(data, pars, gammaTrack): no resampling of fNumIALeft  GammaManager.hh:34 .icc:38-48 */
+#define G4HB200_GOP_UPDATE_NIA 1         /* UpdateNumIALeft(track)                                        .hh:41 .icc:97-105  */
+#define G4HB200_GOP_SELECT_INTERACTION 2 /* SelectInteraction(data, tlData)                               .hh:51 .icc:173-177 */
+#define G4HB200_GOP_PERFORM_SELECTED 3   /* Perform(data, pars, tlData) for an interaction selected before .hh:39 .icc:54-94   */
+int g4hb200_gamma_track_op(G4HB200* h, int op, G4HB200GammaBatch* dev, G4HB200SecondaryQueue* sec, uint64_t seed, void* stream);
 
 /* ---- host-buffer entry points (the call a host application makes) ---------------------------
  * Upload the persistent groups of `host`, run the fused step, download state + results and the

@@ -1,22 +1,15 @@
-"""Pick the strongest available checker (TEST INFRASTRUCTURE; see oracle/README in DESIGN.md).
+"""The checker the smoke test and the bench use (TEST INFRASTRUCTURE).
 
-  1. oracle/_ref/libg4hepem_ref.so -- the unmodified reference compiled from /root/reference (kind "reference")
-  2. oracle/_build/libg4hepem_oracle.so -- the plain-C restatement (kind "port")
+There is one oracle: oracle/_ref/libg4hepem_ref.so, the unmodified reference compiled from /root/reference by
+oracle/Makefile (kind "reference").  It is built where /root/reference exists and travels to the GPU box prebuilt.
 """
-import os
-
 from . import ref as _ref
 
 
 def best_available(json_path):
-    if _ref.available():
-        r = _ref.Reference(json_path)
-        r.kind = "reference"
-        return r
-    from . import port as _port
-
-    if _port.available():
-        p = _port.Port(json_path)
-        p.kind = "port"
-        return p
-    raise RuntimeError("no oracle library built: run __graft_entry__.build()")
+    if not _ref.available():
+        raise RuntimeError(f"no oracle library built ({_ref.REF_LIB} missing): run __graft_entry__.build() where "
+                           "/root/reference exists")
+    r = _ref.Reference(json_path)
+    r.kind = "reference"
+    return r

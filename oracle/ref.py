@@ -37,6 +37,9 @@ _PROTOS = {
     "g4href_electron_step": (C.c_int, [_vp, C.POINTER(_capi.ElectronBatch), C.POINTER(_capi.SecondaryQueue), C.c_uint64, C.c_int]),
     "g4href_gamma_howfar": (C.c_int, [_vp, C.POINTER(_capi.GammaBatch), C.c_uint64, C.c_int]),
     "g4href_gamma_perform": (C.c_int, [_vp, C.POINTER(_capi.GammaBatch), C.POINTER(_capi.SecondaryQueue), C.c_uint64, C.c_int]),
+    "g4href_electron_track_op": (C.c_int, [_vp, C.c_int, C.POINTER(_capi.ElectronBatch), C.POINTER(_capi.SecondaryQueue), C.c_uint64, _vp]),
+    "g4href_electron_check_delta": (C.c_int, [_vp, C.POINTER(_capi.ElectronBatch), _vp, _vp]),
+    "g4href_gamma_track_op": (C.c_int, [_vp, C.c_int, C.POINTER(_capi.GammaBatch), C.POINTER(_capi.SecondaryQueue), C.c_uint64]),
     "g4href_gamma_step": (C.c_int, [_vp, C.POINTER(_capi.GammaBatch), C.POINTER(_capi.SecondaryQueue), C.c_uint64, C.c_int]),
 }
 
@@ -139,3 +142,23 @@ class Reference:
 
     def gamma_step(self, batch, sec, seed, nthreads=1):
         self._run(self.lib.g4href_gamma_step, batch, sec, seed, nthreads)
+
+    # ---- the track-level statics, one at a time (op codes: _capi.OP_*, _capi.GOP_*)
+    def electron_track_op(self, op, batch, seed=0, sec=None, flags=None):
+        s = batch.as_struct()
+        q = sec.as_struct() if sec is not None else None
+        rc = self.lib.g4href_electron_track_op(self.state, op, C.byref(s), C.byref(q) if q is not None else None, seed,
+                                               _p(flags) if flags is not None else None)
+        if rc != 0:
+            raise RuntimeError(f"reference driver returned {rc}")
+
+    def electron_check_delta(self, batch, urnd, flags):
+        s = batch.as_struct()
+        self.lib.g4href_electron_check_delta(self.state, C.byref(s), _p(urnd), _p(flags))
+
+    def gamma_track_op(self, op, batch, seed=0, sec=None):
+        s = batch.as_struct()
+        q = sec.as_struct() if sec is not None else None
+        rc = self.lib.g4href_gamma_track_op(self.state, op, C.byref(s), C.byref(q) if q is not None else None, seed)
+        if rc != 0:
+            raise RuntimeError(f"reference driver returned {rc}")

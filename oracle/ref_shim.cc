@@ -39,6 +39,7 @@
 #include "G4HepEmElectronManager.hh"
 #include "G4HepEmGammaManager.hh"
 #include "G4HepEmElectronInteractionBrem.hh"
+#include "G4HepEmPositronInteractionAnnihilation.hh"
 #include "G4HepEmGammaInteractionConversion.hh"
 #include "G4HepEmRunUtils.hh"
 
@@ -110,6 +111,7 @@ void UnpackElectron(const G4HB200ElectronBatch* b, int64_t i, G4HepEmElectronTra
     msc->fPar1           = b->par12[2 * i];
     msc->fPar2           = b->par12[2 * i + 1];
     msc->fPar3           = b->par3_pad[2 * i];
+    if (b->prestep != nullptr) et.SetPreStepEKin(b->prestep[2 * i], b->prestep[2 * i + 1]);
   }
 }
 
@@ -172,6 +174,10 @@ void PackElectron(G4HB200ElectronBatch* b, int64_t i, G4HepEmElectronTrack& et, 
     b->par12[2 * i + 1]         = msc->fPar2;
     b->par3_pad[2 * i]          = msc->fPar3;
     b->par3_pad[2 * i + 1]      = 0.0;
+    if (b->prestep != nullptr) {
+      b->prestep[2 * i]     = et.GetPreStepEKin();
+      b->prestep[2 * i + 1] = et.GetPreStepLogEKin();
+    }
   }
 }
 
@@ -325,6 +331,68 @@ void GammaRange(RefState* rs, G4HB200GammaBatch* b, uint64_t seed, Mode mode, in
   }
 }
 
+// ---- the track-level statics, one at a time (the pieces G4HepEmTrackingManager::TrackElectron / TrackGamma call) --------------
+// op codes: include/g4hepem_b200.h (G4HB200_OP_*, G4HB200_GOP_*)
+void ElectronOpRange(RefState* rs, int op, G4HB200ElectronBatch* b, uint64_t seed, int32_t* flags, std::vector<SecRecord>* secs) {
+  G4HepEmData* data       = rs->state->fData;
+  G4HepEmParameters* pars = rs->state->fParameters;
+  G4HepEmTLData tl;
+  G4HStream stream{0, 0, 0};
+  G4HepEmRandomEngine eng(&stream);
+  tl.SetRandomEngine(&eng);
+  G4HepEmElectronTrack* et = tl.GetPrimaryElectronTrack();
+  for (int64_t i = 0; i < b->n; ++i) {
+    UnpackElectron(b, i, *et, eng, stream, seed, true);
+    G4HepEmTrack* t = et->GetTrack();
+    bool result = false;
+    switch (op) {
+      case G4HB200_OP_HOWFAR_DISCRETE: G4HepEmElectronManager::HowFarToDiscreteInteraction(data, pars, et); break;
+      case G4HB200_OP_HOWFAR_MSC: G4HepEmElectronManager::HowFarToMSC(data, pars, et, &eng); break;
+      case G4HB200_OP_UPDATE_PSTEP: G4HepEmElectronManager::UpdatePStepLength(et); break;
+      case G4HB200_OP_UPDATE_NIA: G4HepEmElectronManager::UpdateNumIALeft(et); break;
+      case G4HB200_OP_MEAN_ELOSS: result = G4HepEmElectronManager::ApplyMeanEnergyLoss(data, pars, et); break;
+      case G4HB200_OP_SAMPLE_MSC: G4HepEmElectronManager::SampleMSC(data, pars, et, &eng); break;
+      case G4HB200_OP_LOSS_FLUCT: result = G4HepEmElectronManager::SampleLossFluctuations(data, pars, et, &eng); break;
+      case G4HB200_OP_DISCRETE: G4HepEmElectronManager::PerformDiscrete(data, pars, &tl); break;
+      case G4HB200_OP_ANNIHILATE_AT_REST: G4HepEmPositronInteractionAnnihilation::Perform(&tl, true); break;
+      case G4HB200_OP_PERFORM_CONTINUOUS: result = G4HepEmElectronManager::PerformContinuous(data, pars, et, &eng); break;
+      case G4HB200_OP_RESAMPLE_NIA:
+        // the loop at the top of HowFar (G4HepEmElectronManager.icc:39-43) and of TrackElectron (G4HepEmTrackingManager.cc:430-434)
+        for (int ip = 0; ip < 4; ++ip) {
+          if (t->GetNumIALeft(ip) <= 0.) t->SetNumIALeft(-G4HepEmLog(eng.flat()), ip);
+        }
+        break;
+      default: break;
+    }
+    if (flags != nullptr && (op == G4HB200_OP_MEAN_ELOSS || op == G4HB200_OP_LOSS_FLUCT || op == G4HB200_OP_PERFORM_CONTINUOUS))
+      flags[i] = result ? 1 : 0;
+    if (secs != nullptr) CollectSecondaries(tl, i, *secs);
+    PackElectron(b, i, *et, eng, stream);
+  }
+}
+
+void GammaOpRange(RefState* rs, int op, G4HB200GammaBatch* b, uint64_t seed, std::vector<SecRecord>* secs) {
+  G4HepEmData* data       = rs->state->fData;
+  G4HepEmParameters* pars = rs->state->fParameters;
+  G4HepEmTLData tl;
+  G4HStream stream{0, 0, 0};
+  G4HepEmRandomEngine eng(&stream);
+  tl.SetRandomEngine(&eng);
+  G4HepEmGammaTrack* gt = tl.GetPrimaryGammaTrack();
+  for (int64_t i = 0; i < b->n; ++i) {
+    UnpackGamma(b, i, *gt, stream, seed, true);
+    switch (op) {
+      case G4HB200_GOP_HOWFAR_TRACK: G4HepEmGammaManager::HowFar(data, pars, gt); break;
+      case G4HB200_GOP_UPDATE_NIA: G4HepEmGammaManager::UpdateNumIALeft(gt->GetTrack()); break;
+      case G4HB200_GOP_SELECT_INTERACTION: G4HepEmGammaManager::SelectInteraction(data, &tl); break;
+      case G4HB200_GOP_PERFORM_SELECTED: G4HepEmGammaManager::Perform(data, pars, &tl); break;
+      default: break;
+    }
+    if (secs != nullptr) CollectSecondaries(tl, i, *secs);
+    PackGamma(b, i, *gt, stream);
+  }
+}
+
 template <class Batch, class Fn>
 int RunThreaded(RefState* rs, Batch* b, G4HB200SecondaryQueue* sec, uint64_t seed, Mode mode, int nthreads, Fn fn) {
   const int64_t n = b->n;
@@ -469,6 +537,29 @@ void g4href_rng_uniforms(uint64_t seed, int64_t n, const int32_t* trackId, int32
   }
 }
 
+int g4href_electron_track_op(void* p, int op, G4HB200ElectronBatch* b, G4HB200SecondaryQueue* sec, uint64_t seed, int32_t* flags) {
+  std::vector<SecRecord> secs;
+  ElectronOpRange(static_cast<RefState*>(p), op, b, seed, flags, sec != nullptr ? &secs : nullptr);
+  return AppendSecondaries(sec, secs);
+}
+int g4href_electron_check_delta(void* p, G4HB200ElectronBatch* b, const double* urnd, int32_t* flags) {
+  RefState* rs = static_cast<RefState*>(p);
+  G4HepEmTLData tl;
+  G4HStream stream{0, 0, 0};
+  G4HepEmRandomEngine eng(&stream);
+  G4HepEmElectronTrack* et = tl.GetPrimaryElectronTrack();
+  for (int64_t i = 0; i < b->n; ++i) {
+    UnpackElectron(b, i, *et, eng, stream, 0, true);
+    flags[i] = G4HepEmElectronManager::CheckDelta(rs->state->fData, et->GetTrack(), urnd[i]) ? 1 : 0;
+    b->ekin_logekin[2 * i + 1] = PeekLogEKin(et->GetTrack());
+  }
+  return 0;
+}
+int g4href_gamma_track_op(void* p, int op, G4HB200GammaBatch* b, G4HB200SecondaryQueue* sec, uint64_t seed) {
+  std::vector<SecRecord> secs;
+  GammaOpRange(static_cast<RefState*>(p), op, b, seed, sec != nullptr ? &secs : nullptr);
+  return AppendSecondaries(sec, secs);
+}
 int g4href_electron_howfar(void* p, G4HB200ElectronBatch* b, uint64_t seed, int nthreads) {
   return RunThreaded(static_cast<RefState*>(p), b, nullptr, seed, Mode::kHowFar, nthreads, ElectronRange);
 }

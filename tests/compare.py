@@ -12,10 +12,11 @@ ABS_DIR = 1.0e-12
 def rel_close(a, b, rel=REL, abs_tol=0.0):
     a = np.asarray(a, dtype=np.float64)
     b = np.asarray(b, dtype=np.float64)
-    both_nan = np.isnan(a) & np.isnan(b)
     diff = np.abs(a - b)
-    ok = (diff <= rel * np.maximum(np.abs(a), np.abs(b)) + abs_tol) | (a == b) | both_nan
-    return ok
+    with np.errstate(invalid="ignore"):
+        ok = (diff <= rel * np.maximum(np.abs(a), np.abs(b)) + abs_tol) | (a == b)
+    # a NaN never matches (not even another NaN): compared state must be finite
+    return ok & ~(np.isnan(a) | np.isnan(b))
 
 
 def compare_group(name, a, b, kinds, report, mask=None):
@@ -79,12 +80,13 @@ def compare_electron_batches(a, b, handover=True):
     return rep
 
 
-def compare_gamma_batches(a, b):
+def compare_gamma_batches(a, b, pe_mask=None):
     rep = {}
     for g, kinds in GAMMA_KINDS.items():
         compare_group(g, getattr(a, g), getattr(b, g), kinds, rep)
-    # fPEmxSec is defined when PE was selected or the photon is below 2 m_e c^2 (G4HepEmGammaManager.icc:182)
-    pe_defined = (a.winner == 2) | (a.ekin_logekin[:, 0] == 0.0) & (a.winner == 2)
+    # fPEmxSec is defined when PE was selected or the photon was below the upper edge of the second energy window
+    # (gm_emax1 = 2 m_e c^2; G4HepEmGammaManager.icc:118-139,182): callers that know the pre-step energies pass the mask
+    pe_defined = (a.winner == 2) if pe_mask is None else ((a.winner == 2) | pe_mask)
     compare_group("pemxsec", a.edep_pemxsec, b.edep_pemxsec, (None, "rel"), rep, mask=pe_defined)
     for col, nm in enumerate(("imc", "flags", "id", "draws")):
         bad = int((a.meta[:, col] != b.meta[:, col]).sum())

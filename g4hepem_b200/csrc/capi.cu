@@ -3,6 +3,7 @@
 // compute entry point launches a kernel or returns an error.
 #include <cuda_runtime.h>
 
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>

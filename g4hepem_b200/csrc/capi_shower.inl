@@ -184,7 +184,8 @@ int RunStepLoop(G4HB200* h, const G4HB200SlabGeometry* geom, int64_t numPrimarie
     nEl = mixed.nEl;
     nGm = mixed.nGm;
     MixedPopulationKernel<<<OneWave(h, MixedPopulationKernel, numPrimaries), kThreadsPerBlock, 0, st>>>(
-        nEl, nGm, h->view.numMatCut, mixed.emin, mixed.emax, seed, s.el[0], s.elGeo[0], s.gm[0], s.gmGeo[0]);
+        nEl, nGm, h->view.numMatCut, std::log(mixed.emin), std::log(mixed.emax / mixed.emin), seed, s.el[0], s.elGeo[0], s.gm[0],
+        s.gmGeo[0]);
     cudaStreamSynchronize(st);  // the population is an input: keep it out of the timed loop
     cudaEventRecord(ev0, st);
   } else {
@@ -227,7 +228,7 @@ int RunStepLoop(G4HB200* h, const G4HB200SlabGeometry* geom, int64_t numPrimarie
     }
     if (nEl > 0) {
       ShowerSecondaryKernel<<<OneWave(h, ShowerSecondaryKernel, 2 * nEl), kThreadsPerBlock, 0, st>>>(
-          g, seed, s.secEl, s.el[cur].meta, s.elGeo[cur], s.el[nxt], s.elGeo[nxt], s.gm[nxt], s.gmGeo[nxt], s.score);
+          h->view, g, seed, s.secEl, s.el[cur].meta, s.elGeo[cur], s.el[nxt], s.elGeo[nxt], s.gm[nxt], s.gmGeo[nxt], s.score);
       ++h->launches;
       cudaMemcpyAsync(s.pinned + 3, s.secEl.count, sizeof(int32_t), cudaMemcpyDeviceToHost, st);
     } else {
@@ -249,7 +250,7 @@ int RunStepLoop(G4HB200* h, const G4HB200SlabGeometry* geom, int64_t numPrimarie
           g, b, s.gmGeo[cur], s.gm[nxt], s.gmGeo[nxt], s.score);
       ++h->launches;
       ShowerSecondaryKernel<<<OneWave(h, ShowerSecondaryKernel, 2 * nGm), kThreadsPerBlock, 0, sg>>>(
-          g, seed, s.secGm, s.gm[cur].meta, s.gmGeo[cur], s.el[nxt], s.elGeo[nxt], s.gm[nxt], s.gmGeo[nxt], s.score);
+          h->view, g, seed, s.secGm, s.gm[cur].meta, s.gmGeo[cur], s.el[nxt], s.elGeo[nxt], s.gm[nxt], s.gmGeo[nxt], s.score);
       ++h->launches;
       cudaMemcpyAsync(s.pinned + 4, s.secGm.count, sizeof(int32_t), cudaMemcpyDeviceToHost, sg);
     } else {

@@ -589,14 +589,33 @@ __device__ __forceinline__ void ChildStream(uint64_t seed, int parentId, int par
 }
 
 // the parents sit in a batch of one kind: only their meta (id, draw counter), position and volume are needed
+// Secondary production cuts of the caller (StackSecondaries(..., isApplyCuts), G4HepEmTrackingManager.cc:1254-1326, with
+// fIsApplyCuts of the region of the parent's pre-step couple, .cc:426): a secondary below the cut of its kind is not
+// tracked, its kinetic energy (+ 2 m_e c^2 for a positron) is deposited where the parent's step deposits.
+// returns the energy to deposit (> 0: the secondary is dropped)
+G4H_FN double SecondaryBelowCut(const TablesView& tv, int parentImc, int kind, double secEKin) {
+  const int ireg = G4H_LD(tv.mcIreg + parentImc);
+  const bool isApplyCuts = (static_cast<int>(G4H_LD(tv.regionPars + 8 * ireg + kRCallerFlags)) & 2) != 0;
+  if (!isApplyCuts) return 0.0;
+  const double* cuts = tv.mcCuts + 4 * parentImc;
+  if (kind == G4HB200_SEC_ELECTRON) return secEKin < G4H_LD(cuts + kCElCut) ? secEKin : 0.0;
+  if (kind == G4HB200_SEC_POSITRON) {
+    return (kElectronMassC2 < G4H_LD(cuts + kCGamCut) && secEKin < G4H_LD(cuts + kCPosCut)) ? secEKin + 2 * kElectronMassC2 : 0.0;
+  }
+  return secEKin < G4H_LD(cuts + kCGamCut) ? secEKin : 0.0;
+}
+
 __global__ void __launch_bounds__(kThreadsPerBlock)
-ShowerSecondaryKernel(const __grid_constant__ SlabGeom g, uint64_t seed, const __grid_constant__ G4HB200SecondaryQueue q,
-                      const int32_t* __restrict__ parentMeta, const __grid_constant__ TrackGeo pgeo,
-                      const __grid_constant__ G4HB200ElectronBatch ne, const __grid_constant__ TrackGeo negeo,
-                      const __grid_constant__ G4HB200GammaBatch ng, const __grid_constant__ TrackGeo nggeo,
-                      const __grid_constant__ ShowerScore sc) {
+ShowerSecondaryKernel(const __grid_constant__ TablesView tv, const __grid_constant__ SlabGeom g, uint64_t seed,
+                      const __grid_constant__ G4HB200SecondaryQueue q, const int32_t* __restrict__ parentMeta,
+                      const __grid_constant__ TrackGeo pgeo, const __grid_constant__ G4HB200ElectronBatch ne,
+                      const __grid_constant__ TrackGeo negeo, const __grid_constant__ G4HB200GammaBatch ng,
+                      const __grid_constant__ TrackGeo nggeo, const __grid_constant__ ShowerScore sc) {
   __shared__ CtaCounters<2> cc;
+  __shared__ CtaHist hist;
+  const int nbins = g.numLayers * g.numAbsorbers;
   cc.Init();
+  if (g.inheritCouple == 0) hist.Init(nbins);
   const int cnt = q.count[0];
   const int nRound = static_cast<int>(RoundUpToCta(cnt));
   const int stride = gridDim.x * blockDim.x;
@@ -618,6 +637,13 @@ ShowerSecondaryKernel(const __grid_constant__ SlabGeom g, uint64_t seed, const _
       pz  = LoadPair(pgeo.posz_pad, p);
       vol = pgeo.vol[p];
       route = kind == G4HB200_SEC_GAMMA ? 1 : 0;
+      if (g.inheritCouple == 0) {
+        const double cutEdep = SecondaryBelowCut(tv, parentImc, kind, dze.b);
+        if (cutEdep > 0.0) {
+          atomicAdd(&hist.bin[vol], cutEdep);
+          route = -1;
+        }
+      }
     }
     // reserve slots in the two next-step stores
     const unsigned active = 0xffffffffu;
@@ -676,6 +702,7 @@ ShowerSecondaryKernel(const __grid_constant__ SlabGeom g, uint64_t seed, const _
       nggeo.vol[o] = vol;
     }
   }
+  if (g.inheritCouple == 0) hist.Flush(sc.hist, nbins);
 }
 
 // primaries: at the front face of the calorimeter, along +x, entering (on the boundary)
@@ -718,14 +745,17 @@ ShowerPrimaryKernel(const __grid_constant__ SlabGeom g, int64_t n, int kind, dou
 }
 // BASELINE configs[3]: n tracks, one third each e-, e+, gamma, contiguous per particle and, inside a particle,
 // per couple (the queue order a stepping loop keeps); E log-uniform in [emin, emax], isotropic directions, first-step
-// state, not on a boundary.  Inputs of a synthetic workload: libdevice log/exp are fine here.
+// state, not on a boundary.  The population is a pure function of (seed, track index) built from +, *, /, sqrt and the VDT
+// exponential only, so that the CPU driver of the parity test (tests/shower_oracle.py: mixed_population) generates the
+// very same tracks: uniforms of the stream keyed (seed ^ 0x1A2B3C4D, track index): draw 0 energy, 1 cos(theta), 2 safety,
+// 3.. the azimuth by von Neumann's rejection (a point in the unit disc -> cos / sin of twice its polar angle).
+// lmin = log(emin), lrange = log(emax / emin): evaluated by the host (one value for all tracks).
 __global__ void __launch_bounds__(kThreadsPerBlock)
-MixedPopulationKernel(int64_t nEl, int64_t nGm, int numCouples, double emin, double emax, uint64_t seed,
+MixedPopulationKernel(int64_t nEl, int64_t nGm, int numCouples, double lmin, double lrange, uint64_t seed,
                       const __grid_constant__ G4HB200ElectronBatch ne, const __grid_constant__ TrackGeo negeo,
                       const __grid_constant__ G4HB200GammaBatch ng, const __grid_constant__ TrackGeo nggeo) {
   const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
   const int64_t n = nEl + nGm;
-  const double lmin = log(emin), lrange = log(emax / emin);
   for (int64_t t = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; t < n; t += stride) {
     const bool isGamma = t >= nEl;
     const int64_t o = isGamma ? t - nEl : t;
@@ -735,17 +765,24 @@ MixedPopulationKernel(int64_t nEl, int64_t nGm, int numCouples, double emin, dou
     const int64_t kindSize = isGamma ? nGm : (isPositron ? nEl - half : half);
     const int imc = static_cast<int>((inKind * numCouples) / (kindSize > 0 ? kindSize : 1));
     const int id = static_cast<int>(t);
-    const Uniform2 u01 = UniformPair(static_cast<uint32_t>(seed) ^ 0x1A2B3C4Du, static_cast<uint32_t>(seed >> 32), static_cast<uint32_t>(id), 0u);
-    const Uniform2 u23 = UniformPair(static_cast<uint32_t>(seed) ^ 0x1A2B3C4Du, static_cast<uint32_t>(seed >> 32), static_cast<uint32_t>(id), 1u);
-    const double ekin = exp(lmin + u01.a * lrange);
-    const double cost = 2.0 * u01.b - 1.0;
-    const double sint = sqrt((1.0 - cost) * (1.0 + cost));
-    double sphi, cphi;
-    sincos(k2Pi * u23.a, &sphi, &cphi);
+    Rng gen;
+    gen.Init(seed ^ 0x1A2B3C4DULL, static_cast<uint32_t>(id), 0u, false, 0.0);
+    const double ekin   = Exp(lmin + gen.Flat() * lrange);
+    const double cost   = 2.0 * gen.Flat() - 1.0;
+    const double safety = gen.Flat();
+    const double sint   = sqrt((1.0 - cost) * (1.0 + cost));
+    double vx, vy, r2;
+    do {
+      vx = 2.0 * gen.Flat() - 1.0;
+      vy = 2.0 * gen.Flat() - 1.0;
+      r2 = vx * vx + vy * vy;
+    } while (r2 > 1.0 || r2 == 0.0);
+    const double cphi = (vx * vx - vy * vy) / r2;
+    const double sphi = 2.0 * vx * vy / r2;
     if (!isGamma) {
       StorePair(ne.ekin_logekin, o, ekin, 100.0);
       StorePair(ne.dirx_diry, o, sint * cphi, sint * sphi);
-      StorePair(ne.dirz_safety, o, cost, u23.b);
+      StorePair(ne.dirz_safety, o, cost, safety);
       StorePair(ne.nia01, o, -1.0, -1.0);
       StorePair(ne.nia23, o, -1.0, -1.0);
       StorePair(ne.msc_irange_dynrf, o, 1.0e+21, 0.04);

@@ -72,7 +72,7 @@ struct TablesView {
 };
 
 // indices into the packed parameter rows
-enum RegionPar { kRFinalRange = 0, kRDRoverRange, kRLinELossLimit, kRMSCRangeFactor, kRMSCSafetyFactor, kRIsMSCMinimal, kRIsFluct, kRIsMultiSteps };
+enum RegionPar { kRFinalRange = 0, kRDRoverRange, kRLinELossLimit, kRMSCRangeFactor, kRMSCSafetyFactor, kRIsMSCMinimal, kRIsFluct, kRCallerFlags };  // kRCallerFlags: fIsMultipleStepsInMSCTrans + 2 * fIsApplyCuts
 enum MatPar { kMDensityCorFactor = 0, kMElectronDensity, kMRadLength, kMMeanExE, kMZeff, kMZeff23, kMZeffSqrt, kMUMSCPar,
               kMStepMin0, kMStepMin1, kMTail0, kMTail1, kMTail2, kMTail3, kMTheta0, kMTheta1 };
 enum ElemPar { kEZet = 0, kEZet13, kEZet23, kECoulomb, kELogZ, kEZFactor1, kEDeltaMaxLow, kEDeltaMaxHigh, kEILVarS1,

@@ -70,7 +70,7 @@ inline void G4HepEmB200Flatten(const G4HepEmData* data, const G4HepEmParameters*
     const G4HepEmRegionParmeters& r = pars->fParametersPerRegion[i];
     const double v[8] = {r.fFinalRange, r.fDRoverRange, r.fLinELossLimit, r.fMSCRangeFactor, r.fMSCSafetyFactor,
                          r.fIsMSCMinimalStepLimit ? 1.0 : 0.0, r.fIsELossFluctuation ? 1.0 : 0.0,
-                         r.fIsMultipleStepsInMSCTrans ? 1.0 : 0.0};
+                         (r.fIsMultipleStepsInMSCTrans ? 1.0 : 0.0) + (r.fIsApplyCuts ? 2.0 : 0.0)};
     out.regionPars.insert(out.regionPars.end(), v, v + 8);
   }
   t.region_pars = out.regionPars.data();

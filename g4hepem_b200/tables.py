@@ -83,7 +83,7 @@ class FlatTables:
         for r in regs:
             rp += [r["fFinalRange"], r["fDRoverRange"], r["fLinELossLimit"], r["fMSCRangeFactor"], r["fMSCSafetyFactor"],
                    float(bool(r["fIsMSCMinimalStepLimit"])), float(bool(r["fIsELossFluctuation"])),
-                   float(bool(r["fIsMultipleStepsInMSCTrans"]))]
+                   float(bool(r["fIsMultipleStepsInMSCTrans"])) + 2.0 * float(bool(r.get("fIsApplyCuts", True)))]
         t.region_pars = self._pd(rp)
         # couples
         mcs = d["fTheMatCutData"]["fMatCutData"]
@@ -189,6 +189,14 @@ class FlatTables:
 
     def couple_material(self):
         return np.ctypeslib.as_array(self.desc.mc_imat, shape=(self.num_matcut,)).copy()
+
+    def couple_region(self):
+        return np.ctypeslib.as_array(self.desc.mc_ireg, shape=(self.num_matcut,)).copy()
+
+    def region_pars(self):
+        """(num_regions, 8): final_range, dr_over_range, lin_eloss_limit, msc_range_factor, msc_safety_factor,
+        is_msc_minimal_step_limit, is_eloss_fluctuation, caller flags (multiple MSC steps + 2 * apply cuts)"""
+        return np.ctypeslib.as_array(self.desc.region_pars, shape=(int(self.desc.num_regions), 8)).copy()
 
 
 def load_state_json(path):

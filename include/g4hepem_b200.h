@@ -71,7 +71,9 @@ typedef struct G4HB200Tables {
   int32_t num_regions;
   /* per region, G4HepEmRegionParmeters (G4HepEmParameters.hh:24-48): 8 doubles each:
    * final_range, dr_over_range, lin_eloss_limit, msc_range_factor, msc_safety_factor,
-   * is_msc_minimal_step_limit, is_eloss_fluctuation, is_multiple_steps_in_msc_trans (flags as 0/1) */
+   * is_msc_minimal_step_limit, is_eloss_fluctuation (flags as 0/1), caller flags = is_multiple_steps_in_msc_trans
+   * + 2 * is_apply_cuts (the two region parameters only the stepping loop around the managers reads,
+   * G4HepEmTrackingManager.cc:426-427) */
   const double* region_pars;
   /* G4HepEmMatCutData (G4HepEmMatCutData.hh:41-68) */
   int32_t num_matcut;

@@ -173,11 +173,13 @@ def _total_mxsec(reference, seed, imc, ekin, lekin, pe_prev):
     return mx, scratch.edep_pemxsec[:, 1].copy()
 
 
-def _woodcock(reference, slab, calo, couple_material, gm, gm_pos, dirs, seed):
+def _woodcock(reference, slab, calo, couple_material, gm, gm_pos, dirs, seed, max_virtual=WDT_MAX_VIRTUAL_STEPS):
     """G4HepEmWoodcockHelper::KeepTracking (G4HepEmWoodcockHelper.cc:150-300) with the decisions around it in
     G4HepEmTrackingManager::TrackGamma (G4HepEmTrackingManager.cc:955-1032), for the gammas it applies to; the same
     operations in the same order as SlabGammaGeometryStep of g4h_shower.cuh.
-    Returns (wdt mask, physical step, positions, volumes of the wdt tracks after the Woodcock part)."""
+    max_virtual: virtual steps per pass (the device loop ends a pass after kWdtMaxVirtualSteps at a fictitious interaction
+    point); None: the reference's own, uncut loop.
+    Returns (wdt mask, physical step, positions, volumes of the wdt tracks after the Woodcock part, cut mask)."""
     n = gm.n
     ekin = gm.ekin_logekin[:, 0]
     lim = calo.woodcock_ekin_min
@@ -215,7 +217,7 @@ def _woodcock(reference, slab, calo, couple_material, gm, gm_pos, dirs, seed):
     d0 = dirs[idx, 0]
     x0 = gm_pos[idx, 0]
     passes = 0
-    while not stop.all() and passes < WDT_MAX_VIRTUAL_STEPS:
+    while not stop.all() and (max_virtual is None or passes < max_virtual):
         passes += 1
         a = np.flatnonzero(~stop)
         need = wmfp[a] < DBL_MAX
@@ -268,16 +270,34 @@ def _woodcock(reference, slab, calo, couple_material, gm, gm_pos, dirs, seed):
     return on, phys, pos, vol, cut
 
 
+ELECTRON_MASS_C2 = 5.1099890999999997e-01
+
+
 def run(reference, calo, num_primaries, primary_ekin, seed, kind=_capi.SEC_ELECTRON, first_track_id=0, max_steps=0, threads=4,
-        couple_material=None):
+        couple_material=None, tables=None, wdt_max_virtual_steps=WDT_MAX_VIRTUAL_STEPS, mixed=None):
     """Returns (edep[num_layers, num_absorbers], stats) like g4hepem_b200.shower.run.
-    couple_material: material index of every couple (needed with calo.woodcock)."""
+    couple_material: material index of every couple (needed with calo.woodcock).
+    tables: the FlatTables of the run: secondary production cuts of the caller (StackSecondaries(..., isApplyCuts),
+    G4HepEmTrackingManager.cc:1254-1326) are applied where the region of the parent's couple asks for them; None: no cuts.
+    wdt_max_virtual_steps: None = the reference's uncut Woodcock loop (KeepTracking runs until the gamma interacts or reaches
+    the surface); the default mirrors the device loop's passes of at most kWdtMaxVirtualSteps virtual steps, which makes the
+    two loops agree iteration by iteration.
+    mixed: (e-/e+ batch, gamma batch) = the loop of g4hb200_mixed_run (BASELINE configs[3]) instead: that population, no geometry
+    (fused steps: the proposed step is accepted, nothing moves but by the MSC displacement), one scoring cell, a secondary
+    inherits its parent's couple, no production cuts; calo is then the one-cell geometry of capi_shower.inl."""
     slab = Slab(calo)
+    if tables is not None:
+        couple_cuts = tables.couple_cuts()
+        apply_cuts = (tables.region_pars()[:, 7].astype(np.int64) & 2) != 0
+        apply_cuts = apply_cuts[tables.couple_region()]
     hist = np.zeros(slab.nl * slab.na)
     stats = dict(num_steps=0, electron_track_steps=0, gamma_track_steps=0, secondaries=0, peak_electrons=0, peak_gammas=0,
                  leak_electron=0.0, leak_gamma=0.0)
     ids = first_track_id + np.arange(num_primaries, dtype=np.int32)
-    if kind == _capi.SEC_GAMMA:
+    if mixed is not None:
+        el, gm = mixed
+        tables = None
+    elif kind == _capi.SEC_GAMMA:
         el, gm = _new_electrons(0), _new_gammas(num_primaries)
         gm.ekin_logekin[:, 0] = primary_ekin
         gm.dirx_diry[:, 0] = 1.0
@@ -291,8 +311,8 @@ def run(reference, calo, num_primaries, primary_ekin, seed, kind=_capi.SEC_ELECT
         el.meta[:, 0] = slab.couple[0]
         el.meta[:, 1] = _capi.F_MSC_FIRST_STEP | _capi.F_ON_BOUNDARY | (_capi.F_POSITRON if kind == _capi.SEC_POSITRON else 0)
         el.meta[:, 2] = ids
-    el_pos = np.zeros((el.n, 3)); el_pos[:, 0] = slab.xfront
-    gm_pos = np.zeros((gm.n, 3)); gm_pos[:, 0] = slab.xfront
+    el_pos = np.zeros((el.n, 3)); el_pos[:, 0] = 0.0 if mixed is not None else slab.xfront
+    gm_pos = np.zeros((gm.n, 3)); gm_pos[:, 0] = 0.0 if mixed is not None else slab.xfront
     el_vol = np.zeros(el.n, dtype=np.int32)
     gm_vol = np.zeros(gm.n, dtype=np.int32)
 
@@ -307,9 +327,22 @@ def run(reference, calo, num_primaries, primary_ekin, seed, kind=_capi.SEC_ELECT
         cid, cdraw = child_stream(seed, sec.parent_kind[:n, 0], parent_meta[p, 3], slot)
         pos = parent_pos[p]
         vol = parent_vol[p]
-        imc = slab.couple[vol % slab.na]
-        ie = np.flatnonzero(knd != _capi.SEC_GAMMA)
-        ig = np.flatnonzero(knd == _capi.SEC_GAMMA)
+        imc = parent_meta[p, 0] if mixed is not None else slab.couple[vol % slab.na]
+        keep = np.ones(n, dtype=bool)
+        if tables is not None:
+            pimc = parent_meta[p, 0]
+            ek = sec.dirz_ekin[:n, 1]
+            cuts = couple_cuts[pimc]
+            on = apply_cuts[pimc]
+            drop_e = on & (knd == _capi.SEC_ELECTRON) & (ek < cuts[:, 0])
+            drop_p = on & (knd == _capi.SEC_POSITRON) & (ELECTRON_MASS_C2 < cuts[:, 2]) & (ek < cuts[:, 1])
+            drop_g = on & (knd == _capi.SEC_GAMMA) & (ek < cuts[:, 2])
+            cut_edep = np.where(drop_e | drop_g, ek, np.where(drop_p, ek + 2 * ELECTRON_MASS_C2, 0.0))
+            drop = drop_e | drop_p | drop_g
+            np.add.at(hist, vol[drop], cut_edep[drop])
+            keep = ~drop
+        ie = np.flatnonzero((knd != _capi.SEC_GAMMA) & keep)
+        ig = np.flatnonzero((knd == _capi.SEC_GAMMA) & keep)
         ne = _new_electrons(len(ie))
         ne.ekin_logekin[:, 0] = sec.dirz_ekin[:n, 1][ie]
         ne.dirx_diry[...] = sec.dirx_diry[:n][ie]
@@ -338,7 +371,12 @@ def run(reference, calo, num_primaries, primary_ekin, seed, kind=_capi.SEC_ELECT
         stats["peak_gammas"] = max(stats["peak_gammas"], gm.n)
         next_el, next_gm = [], []
         # ---- e-/e+ ------------------------------------------------------------------------------------------------
-        if el.n > 0:
+        if el.n > 0 and mixed is not None:
+            sec = batches.SecondaryHostQueue(2 * el.n)
+            reference.electron_step(el, sec, seed, threads)
+            onb = np.zeros(el.n, dtype=bool)
+            nv = el_vol.copy()
+        elif el.n > 0:
             reference.electron_howfar(el, seed, threads)
             dirs = np.stack([el.dirx_diry[:, 0], el.dirx_diry[:, 1], el.dirz_safety[:, 0]], axis=1)
             dist, nv = slab.distance(el_vol, el_pos, dirs)
@@ -349,6 +387,7 @@ def run(reference, calo, num_primaries, primary_ekin, seed, kind=_capi.SEC_ELECT
             el.meta[:, 1] = np.where(onb, el.meta[:, 1] | _capi.F_ON_BOUNDARY, el.meta[:, 1] & ~_capi.F_ON_BOUNDARY)
             sec = batches.SecondaryHostQueue(2 * el.n)
             reference.electron_perform(el, sec, seed, threads)
+        if el.n > 0:
             # MSC displacement
             disp = np.stack([el.edep_dispx[:, 1], el.dispy_dispz[:, 0], el.dispy_dispz[:, 1]], axis=1)
             d2 = disp[:, 0] * disp[:, 0] + disp[:, 1] * disp[:, 1] + disp[:, 2] * disp[:, 2]
@@ -378,10 +417,16 @@ def run(reference, calo, num_primaries, primary_ekin, seed, kind=_capi.SEC_ELECT
             next_el += [(surv, spos, svol), (ce, cepos, cevol)]
             next_gm += [(cg, cgpos, cgvol)]
         # ---- gamma ------------------------------------------------------------------------------------------------------
-        if gm.n > 0:
+        if gm.n > 0 and mixed is not None:
+            sec = batches.SecondaryHostQueue(2 * gm.n)
+            reference.gamma_step(gm, sec, seed, threads)
+            onb = np.zeros(gm.n, dtype=bool)
+            nv = gm_vol.copy()
+        elif gm.n > 0:
             dirs = np.stack([gm.dirx_diry[:, 0], gm.dirx_diry[:, 1], gm.dirz_nia0[:, 0]], axis=1)
             if getattr(calo, "woodcock", False):
-                wdt, phys, gm_pos, wvol, cut = _woodcock(reference, slab, calo, np.asarray(couple_material), gm, gm_pos, dirs, seed)
+                wdt, phys, gm_pos, wvol, cut = _woodcock(reference, slab, calo, np.asarray(couple_material), gm, gm_pos, dirs, seed,
+                                                         wdt_max_virtual_steps)
                 gm_vol = np.where(wdt, wvol, gm_vol).astype(np.int32)
                 normal = np.flatnonzero(~wdt)
                 if len(normal) > 0:
@@ -414,6 +459,7 @@ def run(reference, calo, num_primaries, primary_ekin, seed, kind=_capi.SEC_ELECT
                 gm.edep_pemxsec[cut, 0] = 0.0
             else:
                 reference.gamma_perform(gm, sec, seed, threads)
+        if gm.n > 0:
             np.add.at(hist, gm_vol, gm.edep_pemxsec[:, 0])
             new_vol = np.where(onb, nv, gm_vol)
             ekin = gm.ekin_logekin[:, 0]
@@ -434,3 +480,77 @@ def run(reference, calo, num_primaries, primary_ekin, seed, kind=_capi.SEC_ELECT
         gm_pos = np.concatenate([p[1] for p in next_gm], axis=0) if next_gm else np.zeros((0, 3))
         gm_vol = np.concatenate([p[2] for p in next_gm]).astype(np.int32) if next_gm else np.zeros(0, dtype=np.int32)
     return hist.reshape(slab.nl, slab.na), stats
+
+
+class MixedCell:
+    """The one-cell geometry g4hb200_mixed_run runs its loop in (capi_shower.inl)."""
+    num_layers = 1
+    absorber_thickness = (1.0,)
+    absorber_couple = (0,)
+    half_yz = 1.0
+    woodcock = False
+
+
+def mixed_population(reference, seed, n_el, n_gm, num_couples, emin, emax):
+    """The population of g4hb200_mixed_run: MixedPopulationKernel of g4h_shower.cuh, operation by operation."""
+    import math
+
+    n = n_el + n_gm
+    t = np.arange(n, dtype=np.int64)
+    ids = t.astype(np.int32)
+    gseed = seed ^ 0x1A2B3C4D
+    lmin, lrange = math.log(emin), math.log(emax / emin)
+
+    def u(k):
+        return uniform_at(gseed, ids, np.full(n, k, dtype=np.int64))
+
+    ekin = reference.vdt_log_exp(lmin + u(0) * lrange)[1]
+    cost = 2.0 * u(1) - 1.0
+    safety = u(2)
+    sint = np.sqrt((1.0 - cost) * (1.0 + cost))
+    vx, vy, r2 = np.zeros(n), np.zeros(n), np.full(n, 2.0)
+    draw = np.full(n, 3, dtype=np.int64)
+    todo = np.ones(n, dtype=bool)
+    while todo.any():
+        k = np.flatnonzero(todo)
+        a = 2.0 * uniform_at(gseed, ids[k], draw[k]) - 1.0
+        b = 2.0 * uniform_at(gseed, ids[k], draw[k] + 1) - 1.0
+        draw[k] += 2
+        vx[k], vy[k] = a, b
+        r2[k] = a * a + b * b
+        todo[k] = (r2[k] > 1.0) | (r2[k] == 0.0)
+    cphi = (vx * vx - vy * vy) / r2
+    sphi = 2.0 * vx * vy / r2
+    is_gamma = t >= n_el
+    o = np.where(is_gamma, t - n_el, t)
+    half = n_el // 2
+    is_pos = ~is_gamma & (o >= half)
+    in_kind = np.where(is_gamma, o, np.where(is_pos, o - half, o))
+    kind_size = np.where(is_gamma, n_gm, np.where(is_pos, n_el - half, half))
+    imc = ((in_kind * num_couples) // np.maximum(kind_size, 1)).astype(np.int32)
+    el = _new_electrons(n_el)
+    e = np.flatnonzero(~is_gamma)
+    el.ekin_logekin[:, 0] = ekin[e]
+    el.dirx_diry[:, 0] = sint[e] * cphi[e]
+    el.dirx_diry[:, 1] = sint[e] * sphi[e]
+    el.dirz_safety[:, 0] = cost[e]
+    el.dirz_safety[:, 1] = safety[e]
+    el.meta[:, 0] = imc[e]
+    el.meta[:, 1] = _capi.F_MSC_FIRST_STEP | np.where(is_pos[e], _capi.F_POSITRON, 0)
+    el.meta[:, 2] = ids[e]
+    gm = _new_gammas(n_gm)
+    g = np.flatnonzero(is_gamma)
+    gm.ekin_logekin[:, 0] = ekin[g]
+    gm.dirx_diry[:, 0] = sint[g] * cphi[g]
+    gm.dirx_diry[:, 1] = sint[g] * sphi[g]
+    gm.dirz_nia0[:, 0] = cost[g]
+    gm.meta[:, 0] = imc[g]
+    gm.meta[:, 2] = ids[g]
+    return el, gm
+
+
+def run_mixed(reference, num_electrons, num_gammas, num_steps, seed, num_couples, emin=1.0e-3, emax=1.0e5, threads=4):
+    """CPU driver of BASELINE configs[3] around the reference's managers: (total deposit, stats) like g4hepem_b200.shower.run_mixed."""
+    el, gm = mixed_population(reference, seed, num_electrons, num_gammas, num_couples, emin, emax)
+    hist, stats = run(reference, MixedCell(), num_electrons + num_gammas, 0.0, seed, max_steps=num_steps, threads=threads, mixed=(el, gm))
+    return float(hist.sum()), stats

@@ -10,9 +10,9 @@ from tests import shower_oracle
 SEED = 2026
 
 
-def test_oracle_loop_conserves_energy(reference):
+def test_oracle_loop_conserves_energy(reference, flat_tables):
     calo = shower.SlabCalorimeter()
-    hist, st = shower_oracle.run(reference, calo, 6, 300.0, SEED)
+    hist, st = shower_oracle.run(reference, calo, 6, 300.0, SEED, tables=flat_tables)
     total = hist.sum() + st["leak_electron"] + st["leak_gamma"]
     # kinetic energy in = deposits + leakage (every e+ of these showers annihilates inside: 2 m_e c^2 taken by the
     # conversion come back as the two annihilation photons)
@@ -22,12 +22,12 @@ def test_oracle_loop_conserves_energy(reference):
     assert hist[:10, 0].sum() > hist[:10, 1].sum()
 
 
-def test_oracle_loop_does_not_depend_on_the_sharding(reference):
+def test_oracle_loop_does_not_depend_on_the_sharding(reference, flat_tables):
     """Streams are keyed by track ids derived from the parent: two halves of the primaries give the whole."""
     calo = shower.SlabCalorimeter(num_layers=20)
-    whole, st = shower_oracle.run(reference, calo, 8, 150.0, SEED)
-    a, sa = shower_oracle.run(reference, calo, 4, 150.0, SEED, first_track_id=0)
-    b, sb = shower_oracle.run(reference, calo, 4, 150.0, SEED, first_track_id=4)
+    whole, st = shower_oracle.run(reference, calo, 8, 150.0, SEED, tables=flat_tables)
+    a, sa = shower_oracle.run(reference, calo, 4, 150.0, SEED, first_track_id=0, tables=flat_tables)
+    b, sb = shower_oracle.run(reference, calo, 4, 150.0, SEED, first_track_id=4, tables=flat_tables)
     np.testing.assert_allclose(a + b, whole, rtol=1e-12, atol=1e-12)
     for k in ("electron_track_steps", "gamma_track_steps", "secondaries"):
         assert sa[k] + sb[k] == st[k]
@@ -46,9 +46,9 @@ def test_child_streams_are_distinct():
 @pytest.mark.gpu
 @pytest.mark.parametrize("kind,nprim,ekin", [(_capi.SEC_ELECTRON, 12, 400.0), (_capi.SEC_GAMMA, 8, 250.0),
                                              (_capi.SEC_POSITRON, 5, 100.0)])
-def test_device_shower_matches_cpu_loop(engine, reference, kind, nprim, ekin):
+def test_device_shower_matches_cpu_loop(engine, reference, flat_tables, kind, nprim, ekin):
     calo = shower.SlabCalorimeter()
-    want, wst = shower_oracle.run(reference, calo, nprim, ekin, SEED, kind=kind, first_track_id=100)
+    want, wst = shower_oracle.run(reference, calo, nprim, ekin, SEED, kind=kind, first_track_id=100, tables=flat_tables)
     got = shower.run(engine, calo, nprim, ekin, SEED, kind=kind, first_track_id=100, capacity=1 << 16)
     for k in ("num_steps", "electron_track_steps", "gamma_track_steps", "secondaries", "peak_electrons", "peak_gammas"):
         assert got.stats[k] == wst[k], (k, got.stats[k], wst[k])
@@ -92,8 +92,8 @@ def test_oracle_loop_with_woodcock_tracking(reference, flat_tables):
     plain = shower.SlabCalorimeter()
     wdt = shower.SlabCalorimeter(woodcock=True)
     mat = flat_tables.couple_material()
-    h0, s0 = shower_oracle.run(reference, plain, 6, 300.0, SEED)
-    h1, s1 = shower_oracle.run(reference, wdt, 6, 300.0, SEED, couple_material=mat)
+    h0, s0 = shower_oracle.run(reference, plain, 6, 300.0, SEED, tables=flat_tables)
+    h1, s1 = shower_oracle.run(reference, wdt, 6, 300.0, SEED, couple_material=mat, tables=flat_tables)
     total = h1.sum() + s1["leak_electron"] + s1["leak_gamma"]
     # kinetic energy in = deposits + leakage, up to 2 m_e c^2 for every e+ that leaves the calorimeter
     missing = (6 * 300.0 - total) / (2 * 0.51099891)
@@ -107,7 +107,7 @@ def test_oracle_loop_with_woodcock_tracking(reference, flat_tables):
 def test_device_shower_with_woodcock_tracking_matches_cpu_loop(engine, reference, flat_tables, kind, nprim, ekin):
     calo = shower.SlabCalorimeter(woodcock=True)
     want, wst = shower_oracle.run(reference, calo, nprim, ekin, SEED, kind=kind, first_track_id=300,
-                                  couple_material=flat_tables.couple_material())
+                                  couple_material=flat_tables.couple_material(), tables=flat_tables)
     got = shower.run(engine, calo, nprim, ekin, SEED, kind=kind, first_track_id=300, capacity=1 << 16)
     for k in ("num_steps", "electron_track_steps", "gamma_track_steps", "secondaries", "peak_electrons", "peak_gammas"):
         assert got.stats[k] == wst[k], (k, got.stats[k], wst[k])
@@ -131,3 +131,37 @@ def test_device_showers_at_scale_keep_the_energy_balance(engine, woodcock):
     # lead takes ~78 % of the deposit, liquid argon ~21 % (sampling fraction of the ATLASbar stack)
     frac = res.edep[:, 0].sum() / res.edep.sum()
     assert 0.7 < frac < 0.85, frac
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("kind,nprim,ekin", [(_capi.SEC_ELECTRON, 10, 400.0), (_capi.SEC_GAMMA, 16, 250.0)])
+def test_device_woodcock_passes_equal_the_uncut_reference_loop(engine, reference, flat_tables, kind, nprim, ekin):
+    """The device loop ends a Woodcock pass after 4 virtual steps at a fictitious interaction point and carries on in the next
+    iteration with the next uniform of the track's stream.  The oracle here does NOT: it runs the reference's KeepTracking loop
+    (G4HepEmWoodcockHelper.cc:150-300) until the gamma interacts or reaches the surface.  The showers must be the same:
+    deposits per cell, leakage, the secondaries created and the e-/e+ population (the number of gamma passes differs)."""
+    calo = shower.SlabCalorimeter(woodcock=True)
+    want, wst = shower_oracle.run(reference, calo, nprim, ekin, SEED, kind=kind, first_track_id=700,
+                                  couple_material=flat_tables.couple_material(), tables=flat_tables, wdt_max_virtual_steps=None)
+    got = shower.run(engine, calo, nprim, ekin, SEED, kind=kind, first_track_id=700, capacity=1 << 16)
+    for k in ("electron_track_steps", "secondaries"):
+        assert got.stats[k] == wst[k], (k, got.stats[k], wst[k])
+    assert got.stats["gamma_track_steps"] >= wst["gamma_track_steps"]  # a cut pass counts as a track-step of its own
+    np.testing.assert_allclose(got.edep, want, rtol=1e-9, atol=1e-9)
+    assert abs(got.stats["leak_electron"] - wst["leak_electron"]) <= 1e-9 * max(1.0, wst["leak_electron"])
+    assert abs(got.stats["leak_gamma"] - wst["leak_gamma"]) <= 1e-9 * max(1.0, wst["leak_gamma"])
+
+
+@pytest.mark.gpu
+def test_mixed_run_matches_cpu_driver_step_by_step(engine, reference, flat_tables):
+    """BASELINE configs[3] (g4hb200_mixed_run: mixed e-/e+/gamma population, consecutive fused steps, secondaries fed back)
+    against a CPU loop around the reference's managers (tests/shower_oracle.py: run_mixed -- the same population generated
+    operation by operation, the same child streams): the populations, the number of secondaries and the deposited energy
+    after every step."""
+    n_el, n_gm = 60000, 30000
+    for steps in (1, 2, 3, 4):
+        want_e, want = shower_oracle.run_mixed(reference, n_el, n_gm, steps, SEED, flat_tables.num_matcut)
+        got_e, got = shower.run_mixed(engine, n_el, n_gm, steps, SEED)
+        for k in ("num_steps", "electron_track_steps", "gamma_track_steps", "secondaries", "peak_electrons", "peak_gammas"):
+            assert got[k] == want[k], (steps, k, got[k], want[k])
+        assert abs(got_e - want_e) <= 1e-9 * want_e, (steps, got_e, want_e)

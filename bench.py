@@ -60,18 +60,21 @@ STAGE_BYTES = {
     "ElSamplerKernel<RelBrem>": (4 + 16 + 3 * 16, 3 * 16 + 16, 1),
     "ElSamplerKernel<Annihilation>": (4 + 16 + 3 * 16, 3 * 16 + 16, 2),
     "ElSamplerKernel<AtRest>": (4 + 16, 16, 2),
+    # the whole step as one persistent launch (g4h_fused.cuh): the caller-visible state in and out; secondaries are added
+    # from the queue counter of the run
+    "ElFusedStepKernel": (READ_BYTES, WRITE_BYTES, 0),
 }
 
 
-def _workload_config(n_tracks, ring):
+def _workload_config(n_tracks):
     return {
         "workload": "BASELINE configs[2]: e-/e+ fused HowFar+Perform step (eloss fluctuation, Urban MSC, "
                     "Moller/Bhabha, SB+RB brem, annihilation), 50/50 e-/e+, E log-uniform 1 keV-100 GeV",
         "tracks_per_step_per_gpu": n_tracks,
         "couples": "synthetic ATLASbar-shaped set (Galactic, Pb, lAr x2 regions) + PbWO4 + water, "
                    "tests/golden/hepem_state.json",
-        "cache": f"each timed step reads its own pristine {n_tracks}-track batch from a ring of {ring} "
-                 "(inputs larger than L2)",
+        "cache": "every timed step works on its own pristine batch out of a ring of batches (inputs larger than L2); "
+                 "the reference arm: its own host copy of the batch per step",
         "seed": SEED,
     }
 
@@ -185,6 +188,22 @@ def make_clock_sampler(index):
         return ClockSampler(index)
 
 
+def _spread_over_cores(local, world):
+    """One slice of the allowed cores per rank (rank r of N gets the r-th N-th of them): eight ranks left on the same cores
+    -- and their pinned staging buffers on the memory of one socket -- is what held the 8-GPU host-buffer number at 1.9x
+    one GPU in round 1 (SCALE_r01).  Called before anything allocates pinned memory (first touch decides its placement)."""
+    if world <= 1 or not hasattr(os, "sched_setaffinity"):
+        return None
+    try:
+        cores = sorted(os.sched_getaffinity(0))
+        per = max(1, len(cores) // world)
+        mine = cores[local * per:(local + 1) * per] or cores
+        os.sched_setaffinity(0, mine)
+        return [mine[0], mine[-1]]
+    except OSError:
+        return None
+
+
 def _dist_env():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -237,7 +256,7 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": _workload_config(n, args.steps),
+        "config": _workload_config(n),
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": ora.kind,
                          "sample": f"{args.steps} passes of G4HepEmElectronManager::HowFar+Perform over the full {n}-track batch, "
                                    f"std::thread x {threads}, wall clock"},
@@ -258,6 +277,7 @@ def run_gpu(args):
         raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: g4hepem_b200 has no CPU fallback")
+    core_range = None if args.no_affinity else _spread_over_cores(local, world)
     torch.cuda.set_device(local)
     dist = None
     if world > 1:
@@ -343,6 +363,86 @@ def run_gpu(args):
     tot, _ = sharding.allreduce_scores(hist.cpu().numpy(), [n], dist, device=torch.device("cuda", local))
     edep_sum = float(tot.sum())
 
+    # ---- sustained load: the same step back to back for >= 1 s (the 20-step region above is a 10 ms burst) -------------------
+    sustained = None
+    if args.sustained_seconds > 0:
+        est = max(elapsed_ms / steps, 1e-3)
+        s_steps = int(args.sustained_seconds * 1e3 / est) + 1
+        in_groups_dev = batches.ElectronHostBatch.PAIR_GROUPS + ("meta",)
+        pristine_dev = eng.ElectronDeviceBatch(n, device=local)
+        pristine_dev.upload(pristine, groups=in_groups_dev)
+        barrier()
+        s_sampler = make_clock_sampler(local) if rank == 0 else None
+        sev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(s_steps)]
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s0.record()
+        for i in range(s_steps):
+            b = ring[i % ring_n]
+            for g in in_groups_dev:  # device-to-device restore of the pristine inputs (outside the per-step events)
+                b.t[g][:n].copy_(pristine_dev.t[g][:n], non_blocking=True)
+            sec.reset()
+            sev[i][0].record()
+            eng.ElectronManager.Step(engine, b, sec, SEED)
+            sev[i][1].record()
+        s1.record()
+        barrier()
+        s_clocks = s_sampler.stop() if s_sampler is not None else None
+        s_wall_ms = s0.elapsed_time(s1)
+        s_ms = float(sum(a.elapsed_time(b) for a, b in sev))
+        if dist is not None:
+            t = torch.tensor([s_ms], dtype=torch.float64, device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            s_ms = float(t.item())
+        sustained = {"value": world * n * s_steps / (s_ms * 1e-3), "unit": UNIT, "loop_seconds": s_wall_ms * 1e-3,
+                     "step_seconds": s_ms * 1e-3, "steps": s_steps, "clocks": s_clocks,
+                     "note": "the step of `value` back to back for >= 1 s, every step on pristine inputs restored device-to-device "
+                             "between the per-step CUDA events; value = tracks / summed step time"}
+        del pristine_dev
+
+    # ---- BASELINE configs[4]: TestEm3 ATLASbar 10 GeV e- showers, primaries sharded over the ranks, the per-layer deposits
+    # summed over ranks by ONE NCCL all_reduce on the device -- inside the timed region ---------------------------------------
+    shower_rec = None
+    if args.shower_primaries > 0:
+        from g4hepem_b200 import shower
+
+        calo = shower.SlabCalorimeter()
+        prim = args.shower_primaries
+        cap = max(1 << 18, prim * 1536)
+        shower.run(engine, calo, min(8, prim), 1000.0, SEED, capacity=1 << 18)  # warm-up: streams, workspaces, kernels
+        hist_dev = torch.zeros(calo.num_cells + 4, dtype=torch.float64, device="cuda")
+        if dist is not None:
+            dist.all_reduce(hist_dev)  # warm-up of the communicator
+        barrier()
+        res = shower.run(engine, calo, prim, 10000.0, SEED, first_track_id=rank * prim, capacity=cap)
+        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        st = res.stats
+        a0.record()
+        hist_dev[:calo.num_cells] = torch.from_numpy(res.edep.ravel()).cuda()
+        hist_dev[calo.num_cells:] = torch.tensor([st["electron_track_steps"], st["gamma_track_steps"], st["leak_electron"],
+                                                  st["leak_gamma"]], dtype=torch.float64, device="cuda")
+        if dist is not None:
+            dist.all_reduce(hist_dev)
+        a1.record()
+        torch.cuda.synchronize()
+        # device time of the loop (CUDA events on the library's stream) + of the collective, max over ranks
+        t_ms = torch.tensor([st["device_ms"] + a0.elapsed_time(a1)], dtype=torch.float64, device="cuda")
+        if dist is not None:
+            dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
+        tot = hist_dev.cpu().numpy()
+        sh_ms = float(t_ms.item())
+        track_steps = float(tot[calo.num_cells] + tot[calo.num_cells + 1])
+        edep_total = float(tot[:calo.num_cells].sum())
+        shower_rec = {
+            "workload": "BASELINE configs[4]: TestEm3 ATLASbar (50 x (2.3 mm Pb + 5.7 mm lAr)) 10 GeV e- showers, stepped until no track "
+                        "is left; primaries sharded over the ranks, per-(layer, absorber) deposits summed by one NCCL all_reduce inside "
+                        "the timed region",
+            "primaries_per_gpu": prim, "value": track_steps / (sh_ms * 1e-3), "unit": "track-steps/s",
+            "showers_per_s": world * prim / (sh_ms * 1e-3), "ms": sh_ms, "allreduce_ms_rank0": a0.elapsed_time(a1),
+            "loop_iterations_rank0": int(st["num_steps"]), "kernel_launches_rank0": int(st["kernel_launches"]),
+            "energy_balance": (edep_total + float(tot[calo.num_cells + 2] + tot[calo.num_cells + 3])) / (world * prim * 10000.0),
+            "scaling": "weak", "n_gpus": world,
+        }
+
     # ---- e2e: host buffers through the C-ABI ---------------------------------------------------------------
     e2e_steps = min(steps, args.e2e_steps)
     work = batches.ElectronHostBatch(n, pinned=True)
@@ -389,26 +489,33 @@ def run_gpu(args):
         stages.append({"kernel": name, "ms": ms, "tracks": items / nl, "bytes": per_launch_bytes,
                        "gbs": per_launch_bytes / (ms * 1e-3) / 1e9 if ms > 0 else None})
     dom = max(stages, key=lambda x: x["ms"])
-    achieved = dom["gbs"]
+    step_gbs = step_bytes / (kernel_ms * 1e-3) / 1e9
+    step_traffic, traffic_src = _traffic_from_profile([x["kernel"] for x in stages])
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": warmup,
         "ms_per_step": elapsed_ms / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f64", "data": "synthetic", "config": _workload_config(n, ring_n),
+        "dtype": "f64", "data": "synthetic", "config": _workload_config(n), "ring_batches": ring_n,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "steps": e2e_steps, "api": "g4hb200_electron_step_host (pinned host batch in, host batch + secondaries out)"},
         "gpu_launches": int(launches),
         "clocks": clocks,
-        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": _traffic_from_profile(dom["kernel"]), "kernel": dom["kernel"], "kernel_ms": dom["ms"],
-                     "algorithmic_bytes_per_launch": dom["bytes"], "peak_source": peak_src,
-                     "kernel_share_of_step": dom["ms"] / sum(x["ms"] for x in stages),
-                     "whole_step": {"algorithmic_bytes": step_bytes, "ms": kernel_ms,
-                                    "gbs": step_bytes / (kernel_ms * 1e-3) / 1e9,
-                                    "frac": step_bytes / (kernel_ms * 1e-3) / 1e9 / peak,
-                                    "secondaries": n_sec},
+        # the roofline of the WHOLE step (all its kernels): algorithmic bytes of the caller-visible state over the CUDA-event
+        # time of a step; the kernel with the longest duration is a sub-record
+        "roofline": {"bound": "hbm", "achieved": step_gbs, "peak": peak, "unit": "GB/s", "frac": step_gbs / peak,
+                     "traffic": step_traffic, "traffic_source": traffic_src, "scope": "whole step (every kernel of g4hb200_electron_step)",
+                     "algorithmic_bytes_per_step": step_bytes, "step_ms": kernel_ms, "secondaries_per_step": n_sec,
+                     "peak_source": peak_src,
+                     "dominant_kernel": {"kernel": dom["kernel"], "kernel_ms": dom["ms"], "achieved": dom["gbs"],
+                                         "frac": dom["gbs"] / peak, "algorithmic_bytes_per_launch": dom["bytes"],
+                                         "share_of_step": dom["ms"] / sum(x["ms"] for x in stages)},
                      "stages": stages},
         "edep_sum_mev_last_step_allreduced": edep_sum,
+        "cpu_cores_of_rank0": core_range,
     }
+    if sustained is not None:
+        line["sustained"] = sustained
+    if shower_rec is not None:
+        line["shower"] = shower_rec
     if not args.no_cpu_baseline and world == 1:
         try:
             v, threads, kind, times = _cpu_reference_rate(min(n, args.cpu_sample), 3)
@@ -424,17 +531,30 @@ def run_gpu(args):
     return 0
 
 
-def _traffic_from_profile(kernel):
-    """dram bytes read+written per launch of `kernel` from the committed `ncu --set full` summary."""
-    path = os.path.join(ROOT, "profiles", "r01c_pipeline_full.json")
-    ncu_name = kernel.replace("<e->", "<0>").replace("<e+>", "<1>")
-    if os.path.exists(path):
+NCU_NAMES = {"ElMSCSampleKernel<e->": "ElMSCSampleKernel<0>", "ElMSCSampleKernel<e+>": "ElMSCSampleKernel<1>",
+             "ElSamplerKernel<AtRest>": "ElSamplerKernel<4>", "ElSamplerKernel<Moller>": "ElSamplerKernel<5>",
+             "ElSamplerKernel<Bhabha>": "ElSamplerKernel<6>", "ElSamplerKernel<SeltzerBerger>": "ElSamplerKernel<7>",
+             "ElSamplerKernel<RelBrem>": "ElSamplerKernel<8>", "ElSamplerKernel<Annihilation>": "ElSamplerKernel<9>",
+             "ElFusedStepKernel": "ElFusedStepKernel<0>"}
+
+
+def _traffic_from_profile(kernels):
+    """dram bytes read + written by one 1M-track step = the sum over its kernels in the committed `ncu --set full` summary
+    (unsplit 1M-track launches).  Returns (bytes or None, file)."""
+    for name in ("r02_pipeline_full.json", "r01c_pipeline_full.json"):
+        path = os.path.join(ROOT, "profiles", name)
+        if not os.path.exists(path):
+            continue
         try:
             with open(path) as f:
-                return json.load(f).get(ncu_name, {}).get("dram_bytes_per_launch")
-        except (OSError, ValueError):
-            return None
-    return None
+                prof = json.load(f)
+            total = 0.0
+            for k in kernels:
+                total += prof[NCU_NAMES.get(k, k)]["dram_bytes_per_launch"]
+            return total, "profiles/" + name
+        except (OSError, ValueError, KeyError):
+            continue
+    return None, None
 
 
 def main():
@@ -447,6 +567,9 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=10)
     ap.add_argument("--cpu-sample", type=int, default=1 << 20)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-affinity", action="store_true", help="leave the CPU affinity of the ranks alone")
+    ap.add_argument("--sustained-seconds", type=float, default=1.0, help="length of the sustained-load loop (0: skip)")
+    ap.add_argument("--shower-primaries", type=int, default=4096, help="BASELINE configs[4] record: primaries per GPU (0: skip)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)

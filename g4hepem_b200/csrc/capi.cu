@@ -110,6 +110,7 @@ struct G4HB200 {
   // workspace of the pipelined Perform (interaction queues, pre-step energies)
   struct WorkSlot {
     ElectronWork work;
+    double* steppreMem = nullptr;
     void* mem = nullptr;
     int64_t cap = 0;
     cudaStream_t stream = nullptr;   // chunk stream of the host entry points
@@ -127,9 +128,15 @@ struct G4HB200 {
   int32_t* pinnedCounts = nullptr;   // [kMaxChunks] secondary counts of the chunks of a host call
   int32_t* chunkCounters = nullptr;  // device, [kMaxChunks]
   static constexpr int kMaxChunks = 256;
-  bool monolith = false;  // G4HB200_MONOLITH=1: the one-kernel-per-step variant (kept for A/B measurements)
-  bool fused = true;      // the step as one persistent launch with CTA-local queues (g4h_fused.cuh); G4HB200_FUSED=0: the
-                          // round-1 pipeline of stage kernels over global queues (kept for A/B measurements)
+  // Two ways to run a step: as the pipeline of stage kernels over global queues (g4h_pipeline.cuh; the default) and as ONE
+  // persistent launch with CTA-local queues (g4h_fused.cuh) for batches below fusedBelow tracks.  Measured on the B200
+  // (tools/size_probe.py, profiles/r02_fused_*): the single launch moves 28 % less through HBM (827 against 1 145 MB per
+  // 1M-track step) but is slower at EVERY batch size (256 tracks: 144 against 114 us, 1M: 0.78 against 0.61 ms): a CTA runs
+  // its stages one after the other with barriers in between, and each stage costs its dependency latency (~3 000 dependent
+  // instructions for the head), while the pipeline runs six samplers side by side and overlaps stages of two half batches.
+  // It stays available for A/B runs: G4HB200_FUSED=1 (always), G4HB200_FUSED_BELOW=n (below n tracks).
+  int64_t fusedBelow = 0;
+  bool Fused(int64_t n) const { return n < fusedBelow; }
   // device batches of at least this many tracks run as two half-batch pipelines side by side (G4HB200_SPLIT_MIN)
   int64_t splitThreshold = 1 << 18;
   int splitParts = 2;  // G4HB200_SPLIT_PARTS, at most kNumSlots
@@ -252,31 +259,12 @@ G4HB200SecondaryQueue NullQueue() {
   return q;
 }
 
-template <int kMode>
-int LaunchElectron(G4HB200* h, G4HB200ElectronBatch* dev, G4HB200SecondaryQueue* sec, uint64_t seed, void* stream) {
-  int rc = CheckHandle(h);
-  if (rc != 0) return rc;
-  if (dev == nullptr || dev->n < 0) return Fail(G4HB200_EINVAL, "bad electron batch");
-  if (kMode != 0 && sec == nullptr) return Fail(G4HB200_EINVAL, "secondary queue required");
-  if (dev->n == 0) return 0;
-  const G4HB200SecondaryQueue q = sec != nullptr ? *sec : NullQueue();
-  const int grid = OneWave(h, ElectronKernel<kMode>, dev->n);
-  ElectronKernel<kMode><<<grid, kThreadsPerBlock, 0, static_cast<cudaStream_t>(stream)>>>(h->view, *dev, q, seed);
-  ++h->launches;
-  G4H_CUDA(cudaGetLastError());
-  return 0;
-}
-
-template <int kMode>
-int LaunchGamma(G4HB200* h, G4HB200GammaBatch* dev, G4HB200SecondaryQueue* sec, uint64_t seed, void* stream) {
+int LaunchGammaHowFar(G4HB200* h, G4HB200GammaBatch* dev, uint64_t seed, void* stream) {
   int rc = CheckHandle(h);
   if (rc != 0) return rc;
   if (dev == nullptr || dev->n < 0) return Fail(G4HB200_EINVAL, "bad gamma batch");
-  if (kMode != 0 && sec == nullptr) return Fail(G4HB200_EINVAL, "secondary queue required");
   if (dev->n == 0) return 0;
-  const G4HB200SecondaryQueue q = sec != nullptr ? *sec : NullQueue();
-  const int grid = OneWave(h, GammaKernel<kMode>, dev->n);
-  GammaKernel<kMode><<<grid, kThreadsPerBlock, 0, static_cast<cudaStream_t>(stream)>>>(h->view, *dev, q, seed);
+  GammaHowFarKernel<<<OneWave(h, GammaHowFarKernel, dev->n), kThreadsPerBlock, 0, static_cast<cudaStream_t>(stream)>>>(h->view, *dev, seed);
   ++h->launches;
   G4H_CUDA(cudaGetLastError());
   return 0;
@@ -292,11 +280,14 @@ int EnsureElectronWork(G4HB200::WorkSlot& slot, int64_t n) {
     slot.cap = 0;
   }
   const size_t cap = static_cast<size_t>((n + 255) & ~static_cast<int64_t>(255));
-  const size_t bytes = cap * 16 + static_cast<size_t>(kNumElQueues) * cap * 4 + 256;
+  const size_t bytes = 2 * cap * 16 + static_cast<size_t>(kNumElQueues) * cap * 4 + 256;
   const cudaError_t err = cudaMalloc(&slot.mem, bytes);
   if (err != cudaSuccess) return Fail(G4HB200_ENOMEM, "cudaMalloc(workspace)", err);
   unsigned char* p = static_cast<unsigned char*>(slot.mem);
   slot.work.prestep = reinterpret_cast<double*>(p);
+  p += cap * 16;
+  slot.work.steppre = nullptr;  // set by the stepping loop only (MSC sub-steps: the energy at the beginning of the whole step)
+  slot.steppreMem   = reinterpret_cast<double*>(p);
   p += cap * 16;
   for (int k = 0; k < kNumElQueues; ++k) {
     slot.work.queue[k] = reinterpret_cast<int32_t*>(p);
@@ -409,7 +400,8 @@ int LaunchElectronPipeline(G4HB200* h, G4HB200ElectronBatch* dev, G4HB200Seconda
   if ((rc = EnsureElectronWork(h->slots[slotIndex], dev->n)) != 0) return rc;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int64_t n = dev->n;
-  const ElectronWork& w = h->slots[slotIndex].work;
+  ElectronWork w = h->slots[slotIndex].work;
+  if (slab != nullptr) w.steppre = h->slots[slotIndex].steppreMem;
   G4H_CUDA(cudaMemsetAsync(w.count, 0, kNumElQueues * sizeof(int32_t), st));
   StageTimer t{h, st};
   G4H_CUDA(t.Begin(dev->n));
@@ -590,14 +582,18 @@ int LaunchElectronFused(G4HB200* h, G4HB200ElectronBatch* dev, G4HB200SecondaryQ
     G4HB200SecondaryQueue q = *sec;
     q.parent_base = sec->parent_base + static_cast<int32_t>(lo);
     double* prestep = h->slots[slotIndex].work.prestep + 2 * lo;
+    double* steppre = h->slots[slotIndex].steppreMem + 2 * lo;
     if (slab != nullptr) {
       TrackGeo geo = slab->geo;
       geo.posx_posy += 2 * lo;
       geo.posz_pad += 2 * lo;
       geo.vol += lo;
       geo.nextVol += lo;
-      ShowerElectronFusedKernel<<<FusedGrid(h, ShowerElectronFusedKernel, len), kThreadsPerBlock, 0, st>>>(h->view, part, prestep, q, seed,
-                                                                                                       slab->g, geo);
+      geo.sub_left_eloss += 2 * lo;
+      geo.sub_pre += 2 * lo;
+      geo.sub_range_proc += 2 * lo;
+      ShowerElectronFusedKernel<<<FusedGrid(h, ShowerElectronFusedKernel, len), kThreadsPerBlock, 0, st>>>(h->view, part, prestep, steppre, q,
+                                                                                                       seed, slab->g, geo);
     } else {
       ElFusedStepKernel<kPerformOnly><<<FusedGrid(h, ElFusedStepKernel<kPerformOnly>, len), kThreadsPerBlock, 0, st>>>(h->view, part, prestep,
                                                                                                                  q, seed);
@@ -707,6 +703,9 @@ int LaunchElectronPipelineHalves(G4HB200* h, G4HB200ElectronBatch* dev, G4HB200S
       partSlab.geo.posz_pad += 2 * lo;
       partSlab.geo.vol += lo;
       partSlab.geo.nextVol += lo;
+      partSlab.geo.sub_left_eloss += 2 * lo;
+      partSlab.geo.sub_pre += 2 * lo;
+      partSlab.geo.sub_range_proc += 2 * lo;
     }
     if ((rc = LaunchElectronPipeline<kFused>(h, &part, &q, seed, ps, p, slab != nullptr ? &partSlab : nullptr)) != 0) return rc;
   }
@@ -880,9 +879,8 @@ int g4hb200_create(const G4HB200Tables* tables, int device, G4HB200** out) {
   }
   h->view = MakeView(d);
   {
-    const char* mono = std::getenv("G4HB200_MONOLITH");
-    h->monolith = mono != nullptr && mono[0] == '1';
-    if (const char* fu = std::getenv("G4HB200_FUSED")) h->fused = fu[0] != '0';
+    if (const char* fu = std::getenv("G4HB200_FUSED")) h->fusedBelow = fu[0] != '0' ? (int64_t{1} << 62) : 0;
+    if (const char* fb = std::getenv("G4HB200_FUSED_BELOW")) h->fusedBelow = std::atoll(fb);
     if (const char* sp = std::getenv("G4HB200_SPLIT_MIN")) h->splitThreshold = std::atoll(sp);
     if (const char* sp = std::getenv("G4HB200_SPLIT_PARTS")) {
       const int v = std::atoi(sp);
@@ -1223,30 +1221,25 @@ int g4hb200_rng_uniforms(G4HB200* h, uint64_t seed, int64_t n, const int32_t* tr
 }
 
 int g4hb200_electron_howfar(G4HB200* h, G4HB200ElectronBatch* dev, uint64_t seed, void* stream) {
-  if (h != nullptr && h->monolith) return LaunchElectron<0>(h, dev, nullptr, seed, stream);
   return LaunchElectronHowFar(h, dev, seed, stream);
 }
 int g4hb200_electron_perform(G4HB200* h, G4HB200ElectronBatch* dev, G4HB200SecondaryQueue* sec, uint64_t seed, void* stream) {
-  if (h != nullptr && h->monolith) return LaunchElectron<1>(h, dev, sec, seed, stream);
-  if (h != nullptr && h->fused) return LaunchElectronFused<true>(h, dev, sec, seed, stream);
+  if (h != nullptr && dev != nullptr && h->Fused(dev->n)) return LaunchElectronFused<true>(h, dev, sec, seed, stream);
   return LaunchElectronPipelineHalves<false>(h, dev, sec, seed, stream);
 }
 int g4hb200_electron_step(G4HB200* h, G4HB200ElectronBatch* dev, G4HB200SecondaryQueue* sec, uint64_t seed, void* stream) {
-  if (h != nullptr && h->monolith) return LaunchElectron<2>(h, dev, sec, seed, stream);
-  if (h != nullptr && h->fused) return LaunchElectronFused<false>(h, dev, sec, seed, stream);
+  if (h != nullptr && dev != nullptr && h->Fused(dev->n)) return LaunchElectronFused<false>(h, dev, sec, seed, stream);
   return LaunchElectronPipelineHalves<true>(h, dev, sec, seed, stream);
 }
 int g4hb200_gamma_howfar(G4HB200* h, G4HB200GammaBatch* dev, uint64_t seed, void* stream) {
-  return LaunchGamma<0>(h, dev, nullptr, seed, stream);
+  return LaunchGammaHowFar(h, dev, seed, stream);
 }
 int g4hb200_gamma_perform(G4HB200* h, G4HB200GammaBatch* dev, G4HB200SecondaryQueue* sec, uint64_t seed, void* stream) {
-  if (h != nullptr && h->monolith) return LaunchGamma<1>(h, dev, sec, seed, stream);
-  if (h != nullptr && h->fused) return LaunchGammaFused<1>(h, dev, sec, seed, stream);
+  if (h != nullptr && dev != nullptr && h->Fused(dev->n)) return LaunchGammaFused<1>(h, dev, sec, seed, stream);
   return LaunchGammaPipelineHalves<1>(h, dev, sec, seed, stream);
 }
 int g4hb200_gamma_step(G4HB200* h, G4HB200GammaBatch* dev, G4HB200SecondaryQueue* sec, uint64_t seed, void* stream) {
-  if (h != nullptr && h->monolith) return LaunchGamma<2>(h, dev, sec, seed, stream);
-  if (h != nullptr && h->fused) return LaunchGammaFused<2>(h, dev, sec, seed, stream);
+  if (h != nullptr && dev != nullptr && h->Fused(dev->n)) return LaunchGammaFused<2>(h, dev, sec, seed, stream);
   return LaunchGammaPipelineHalves<2>(h, dev, sec, seed, stream);
 }
 
@@ -1378,7 +1371,7 @@ int g4hb200_electron_step_host(G4HB200* h, G4HB200ElectronBatch* host, G4HB200Se
     q.parent_base = static_cast<int32_t>(lo);
     // H2D: the 7 persistent groups + meta (128 B / track)
     if ((rc = CopyElectron(&hv, &dv, cudaMemcpyHostToDevice, slot.stream, 0, 7, true, false)) != 0) return rc;
-    if ((rc = h->fused ? LaunchElectronFused<false>(h, &dv, &q, seed, slot.stream, nullptr, c % G4HB200::kNumSlots)
+    if ((rc = h->Fused(len) ? LaunchElectronFused<false>(h, &dv, &q, seed, slot.stream, nullptr, c % G4HB200::kNumSlots)
                        : LaunchElectronPipeline<true>(h, &dv, &q, seed, slot.stream, c % G4HB200::kNumSlots)) != 0)
       return rc;
     // D2H: persistent + result groups + meta + winner (180 B / track)
@@ -1439,7 +1432,7 @@ int g4hb200_gamma_step_host(G4HB200* h, G4HB200GammaBatch* host, G4HB200Secondar
   cudaStream_t st = h->stream;
   if ((rc = CopyGamma(host, &h->gmDev, cudaMemcpyHostToDevice, st, 0, 3, true, false)) != 0) return rc;
   if ((rc = g4hb200_secondary_queue_reset(h, &h->secDev, st)) != 0) return rc;
-  if ((rc = h->fused ? LaunchGammaFused<2>(h, &h->gmDev, &h->secDev, seed, st) : LaunchGammaPipeline<2>(h, &h->gmDev, &h->secDev, seed, st)) != 0)
+  if ((rc = h->Fused(n) ? LaunchGammaFused<2>(h, &h->gmDev, &h->secDev, seed, st) : LaunchGammaPipeline<2>(h, &h->gmDev, &h->secDev, seed, st)) != 0)
     return rc;
   if ((rc = CopyGamma(&h->gmDev, host, cudaMemcpyDeviceToHost, st, 0, 5, true, true)) != 0) return rc;
   if ((rc = g4hb200_secondary_queue_download(h, &h->secDev, hostSec, st)) != 0) return rc;

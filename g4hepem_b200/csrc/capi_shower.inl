@@ -13,11 +13,21 @@ struct ShowerStore {
   int32_t* pinned = nullptr;  // {next e-, next gamma, overflow, secondaries e-, secondaries gamma}
 };
 
-int CarveGeo(unsigned char*& p, int64_t cap, TrackGeo& g) {
+// withSubSteps: the e-/e+ stores also carry the MSC sub-step state (TrackGeo::sub_*)
+int CarveGeo(unsigned char*& p, int64_t cap, TrackGeo& g, bool withSubSteps) {
   g.posx_posy = reinterpret_cast<double*>(p);
   p += cap * 16;
   g.posz_pad = reinterpret_cast<double*>(p);
   p += cap * 16;
+  g.sub_left_eloss = g.sub_pre = g.sub_range_proc = nullptr;
+  if (withSubSteps) {
+    g.sub_left_eloss = reinterpret_cast<double*>(p);
+    p += cap * 16;
+    g.sub_pre = reinterpret_cast<double*>(p);
+    p += cap * 16;
+    g.sub_range_proc = reinterpret_cast<double*>(p);
+    p += cap * 16;
+  }
   g.vol = reinterpret_cast<int32_t*>(p);
   p += cap * 4;
   g.nextVol = reinterpret_cast<int32_t*>(p);
@@ -134,12 +144,13 @@ int RunStepLoop(G4HB200* h, const G4HB200SlabGeometry* geom, int64_t numPrimarie
   if ((rc = g4hb200_secondary_queue_alloc(h, 2 * capacity, &s.secGm)) != 0) return fail(rc);
   {
     const size_t per = static_cast<size_t>(capacity) * 40;
-    if (cudaMalloc(&s.geoMem, 4 * per) != cudaSuccess) return fail(Fail(G4HB200_ENOMEM, "cudaMalloc(shower geo)"));
+    const size_t sub = static_cast<size_t>(capacity) * 48;
+    if (cudaMalloc(&s.geoMem, 4 * per + 2 * sub) != cudaSuccess) return fail(Fail(G4HB200_ENOMEM, "cudaMalloc(shower geo)"));
     unsigned char* p = static_cast<unsigned char*>(s.geoMem);
-    CarveGeo(p, capacity, s.elGeo[0]);
-    CarveGeo(p, capacity, s.elGeo[1]);
-    CarveGeo(p, capacity, s.gmGeo[0]);
-    CarveGeo(p, capacity, s.gmGeo[1]);
+    CarveGeo(p, capacity, s.elGeo[0], true);
+    CarveGeo(p, capacity, s.elGeo[1], true);
+    CarveGeo(p, capacity, s.gmGeo[0], false);
+    CarveGeo(p, capacity, s.gmGeo[1], false);
     const size_t sbytes = static_cast<size_t>(nbins) * 8 + 2 * 8 + 4 * 4;
     if (cudaMalloc(&s.scoreMem, sbytes) != cudaSuccess) return fail(Fail(G4HB200_ENOMEM, "cudaMalloc(shower score)"));
     unsigned char* q = static_cast<unsigned char*>(s.scoreMem);
@@ -218,7 +229,7 @@ int RunStepLoop(G4HB200* h, const G4HB200SlabGeometry* geom, int64_t numPrimarie
         // HowFar + geometry step + Perform: the head of the pipeline does the first two and the along-step part of
         // the third in one pass (ShowerElectronHeadKernel), the queue kernels of Perform follow
         const SlabHead slab{g, s.elGeo[cur]};
-        if ((status = h->fused ? LaunchElectronFused<false>(h, &b, &s.secEl, seed, st, &slab)
+        if ((status = h->Fused(nEl) ? LaunchElectronFused<false>(h, &b, &s.secEl, seed, st, &slab)
                                : LaunchElectronPipelineHalves<true>(h, &b, &s.secEl, seed, st, &slab)) != 0)
           break;
       }
@@ -242,7 +253,7 @@ int RunStepLoop(G4HB200* h, const G4HB200SlabGeometry* geom, int64_t numPrimarie
       } else {
         // HowFar + geometry step + SelectInteraction / Perform: one head kernel (ShowerGammaHeadKernel), then the samplers
         const SlabHead slab{g, s.gmGeo[cur]};
-        if ((status = h->fused ? LaunchGammaFused<2>(h, &b, &s.secGm, seed, sg, &slab)
+        if ((status = h->Fused(nGm) ? LaunchGammaFused<2>(h, &b, &s.secGm, seed, sg, &slab)
                                : LaunchGammaPipelineHalves<2>(h, &b, &s.secGm, seed, sg, &slab)) != 0)
           break;
       }

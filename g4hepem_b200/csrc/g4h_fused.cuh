@@ -111,9 +111,16 @@ __device__ __forceinline__ int FusedTilesOfCta(int64_t n) {
 
 // ---- e-/e+ ----------------------------------------------------------------------------------------------------------
 // Geometry: NoGeometryStep (g4hb200_electron_step) or the slab step of the stepping loop (g4h_shower.cuh)
-// kPerformOnly: HowFar ran as its own call (g4hb200_electron_perform): the head is the along-step stage alone
-template <bool kPerformOnly, class MakeGeometry>
-__device__ __forceinline__ void ElFusedBody(const TablesView& tv, const G4HB200ElectronBatch& b, double* prestep,
+// kHead: kHeadStep = HowFar + along-step (g4hb200_electron_step); kHeadPerform = HowFar ran as its own call
+// (g4hb200_electron_perform): the along-step stage alone; kHeadLoop = the head of the stepping loop with the geometry step and the
+// MSC sub-step accounting inside (g4h_shower.cuh: StageLoopHead; steppre: its second workspace)
+enum FusedHead { kHeadStep = 0, kHeadPerform, kHeadLoop };
+template <class GeometryStep>
+G4H_FN int StageLoopHead(const TablesView& tv, const G4HB200ElectronBatch& b, double* prestep, double* steppre, int64_t i,
+                         uint64_t seed, const GeometryStep& geometry);
+
+template <int kHead, class MakeGeometry>
+__device__ __forceinline__ void ElFusedBody(const TablesView& tv, const G4HB200ElectronBatch& b, double* prestep, double* steppre,
                                             const G4HB200SecondaryQueue& sq, uint64_t seed, const MakeGeometry& makeGeometry) {
   __shared__ FusedShared sh;
   if (threadIdx.x < kNumElQueues) sh.cnt[threadIdx.x] = 0;
@@ -140,17 +147,21 @@ __device__ __forceinline__ void ElFusedBody(const TablesView& tv, const G4HB200E
     switch (action) {
       case kFusedHead: {
         int route = -1;
-        if (has) route = kPerformOnly ? StageAlongStep(tv, b, prestep, i) : StageStepHead(tv, b, prestep, i, seed, makeGeometry());
+        if (has) {
+          if constexpr (kHead == kHeadPerform) route = StageAlongStep(tv, b, prestep, i);
+          if constexpr (kHead == kHeadStep) route = StageStepHead(tv, b, prestep, i, seed, makeGeometry());
+          if constexpr (kHead == kHeadLoop) route = StageLoopHead(tv, b, prestep, steppre, i, seed, makeGeometry());
+        }
         FusedRoute<kQMscEl, 5>(sh, route, entry);
         break;
       }
       case kQMscEl: {
-        const int route = has ? StageMSCSample<false>(tv, b, prestep, i, seed, cbeta1) : -1;
+        const int route = has ? StageMSCSample<false>(tv, b, prestep, i, seed, cbeta1, steppre) : -1;
         FusedRoute<kQFluct, 3>(sh, route, entry);
         break;
       }
       case kQMscPos: {
-        const int route = has ? StageMSCSample<true>(tv, b, prestep, i, seed, cbeta1) : -1;
+        const int route = has ? StageMSCSample<true>(tv, b, prestep, i, seed, cbeta1, steppre) : -1;
         FusedRoute<kQFluct, 3>(sh, route, entry);
         break;
       }
@@ -194,7 +205,7 @@ template <bool kPerformOnly>
 __global__ void __launch_bounds__(kThreadsPerBlock, G4H_MINB_FUSED)
 ElFusedStepKernel(const __grid_constant__ TablesView tv, const __grid_constant__ G4HB200ElectronBatch b, double* prestep,
                   const __grid_constant__ G4HB200SecondaryQueue sq, uint64_t seed) {
-  ElFusedBody<kPerformOnly>(tv, b, prestep, sq, seed, MakeNoGeometry{});
+  ElFusedBody<kPerformOnly ? kHeadPerform : kHeadStep>(tv, b, prestep, nullptr, sq, seed, MakeNoGeometry{});
 }
 
 // ---- gamma ----------------------------------------------------------------------------------------------------------

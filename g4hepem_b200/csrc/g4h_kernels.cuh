@@ -14,14 +14,8 @@
 namespace g4h {
 
 constexpr int kThreadsPerBlock = 256;
-// resident CTAs per SM the big kernels are compiled for (register cap = 65536 / (256 * k)); tuned on the B200,
+// resident CTAs per SM the queue kernels are compiled for (register cap = 65536 / (256 * k)); tuned on the B200,
 // see profiles/
-#ifndef G4H_MINB_HOWFAR
-#define G4H_MINB_HOWFAR 2
-#endif
-#ifndef G4H_MINB_CONT
-#define G4H_MINB_CONT 2
-#endif
 #ifndef G4H_MINB_QUEUE
 #define G4H_MINB_QUEUE 3
 #endif
@@ -108,67 +102,17 @@ __device__ __forceinline__ void RouteToQueues(CtaCounters<K>& cc, int route, int
   if (route >= 0) queues[route][cc.base[route] + offset] = value;
 }
 
-// ---- e-/e+ ---------------------------------------------------------------------------------------------------
-// mode 0: HowFar, 1: Perform, 2: fused HowFar + Perform
-template <int kMode>
-__global__ void __launch_bounds__(kThreadsPerBlock, kMode == 0 ? G4H_MINB_HOWFAR : 1)
-ElectronKernel(const __grid_constant__ TablesView tv, const __grid_constant__ G4HB200ElectronBatch b,
-               const __grid_constant__ G4HB200SecondaryQueue q, uint64_t seed) {
-  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
-  // the loop bound is rounded up to a full CTA so that whole CTAs reach the aggregated append
-  const int64_t nRound = RoundUpToCta(b.n);
-  __shared__ CtaCounters<1> cc;
-  if (kMode != 0) cc.Init();
-  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < nRound; i += stride) {
-    const bool valid = i < b.n;
-    ElectronState s;
-    Rng rng;
-    Secondaries sec;
-    sec.n = 0;
-    if (valid) {
-      LoadElectron(b, i, seed, s, rng);
-      if (kMode == 1) LoadElectronHandOver(b, i, s);
-      if (kMode != 1) {
-        ResampleNumIALeft(s, rng);
-        HowFarToDiscreteInteraction(tv, s);
-        HowFarToMSC(tv, s, rng);
-      }
-      if (kMode != 0) {
-        ElectronPerform(tv, s, rng, sec);
-      }
-      StoreElectron(b, i, s, rng);
-      if (kMode == 0) StoreElectronHandOver(b, i, s);
-      // Perform re-converts the geometrical step when geometry cut it (UpdatePStepLength): fTrueStepLength / fZPathLength
-      if (kMode == 1) StorePair(b.tstep_zpath, i, s.trueStep, s.zPath);
-    }
-    if (kMode != 0) AppendSecondaries(cc, q, sec, valid ? s.id : 0, i);
-  }
-}
-
-// ---- gamma -------------------------------------------------------------------------------------------------------
-template <int kMode>
+// ---- gamma HowFar (G4HepEmGammaManager::HowFar(data, pars, tlData), .icc:27-48): one pass over every track --------------------
 __global__ void __launch_bounds__(kThreadsPerBlock)
-GammaKernel(const __grid_constant__ TablesView tv, const __grid_constant__ G4HB200GammaBatch b,
-            const __grid_constant__ G4HB200SecondaryQueue q, uint64_t seed) {
+GammaHowFarKernel(const __grid_constant__ TablesView tv, const __grid_constant__ G4HB200GammaBatch b, uint64_t seed) {
   const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
-  const int64_t nRound = RoundUpToCta(b.n);
-  __shared__ CtaCounters<1> cc;
-  if (kMode != 0) cc.Init();
-  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < nRound; i += stride) {
-    const bool valid = i < b.n;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < b.n; i += stride) {
     GammaState s;
     Rng rng;
-    Secondaries sec;
-    sec.n = 0;
-    if (valid) {
-      LoadGamma(b, i, seed, s, rng);
-      const int flags = b.meta[4 * i + 1];
-      if (kMode == 1) LoadGammaHandOver(b, i, s);
-      if (kMode != 1) GammaHowFar(tv, s, rng);
-      if (kMode != 0) GammaPerform(tv, s, rng, sec);
-      StoreGamma(b, i, s, rng, flags);
-    }
-    if (kMode != 0) AppendSecondaries(cc, q, sec, valid ? s.id : 0, i);
+    LoadGamma(b, i, seed, s, rng);
+    const int flags = b.meta[4 * i + 1];
+    GammaHowFar(tv, s, rng);
+    StoreGamma(b, i, s, rng, flags);
   }
 }
 

@@ -114,7 +114,7 @@ ElMSCSampleKernel(const __grid_constant__ TablesView tv, const __grid_constant__
     int32_t i = 0;
     if (q < cnt) {
       i = queue[q];
-      route = StageMSCSample<kPositron>(tv, b, w.prestep, i, seed, cbeta1);
+      route = StageMSCSample<kPositron>(tv, b, w.prestep, i, seed, cbeta1, w.steppre);
     }
     // kQFluct, kQDiscrete, kQAtRest are three consecutive queues
     RouteToQueues<3>(cc, route < 0 ? -1 : route - kQFluct, i, w.queue + kQFluct, w.count + kQFluct);

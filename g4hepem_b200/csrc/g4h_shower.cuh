@@ -47,6 +47,11 @@ struct TrackGeo {
   double* posz_pad;   // pairs {z, unused}
   int32_t* vol;       // layer * numAbsorbers + absorber; -1: outside
   int32_t* nextVol;   // volume behind the face the step ended on (only meaningful while on a boundary)
+  // e-/e+ stores: what TrackElectron keeps in local variables across the MSC sub-steps of one step (G4HepEmTrackingManager.cc:
+  // 438-445, 574-596), meaningful while G4HB200_F_MSC_SUBSTEP is set; NULL in the gamma stores
+  double* sub_left_eloss;  // pairs {stepLimitLeft, totalEloss}
+  double* sub_pre;         // pairs {preStepEkin, preStepLogEkin} of the whole step
+  double* sub_range_proc;  // pairs {range left after the sub-steps so far, iDProc (the discrete winner MSC replaced)}
 };
 
 struct ShowerScore {
@@ -304,9 +309,138 @@ ShowerElectronHeadKernel(const __grid_constant__ TablesView tv, const __grid_con
   cc.Init();
   const SlabGeometryStep geometry{g, geo, b.dirx_diry};
   for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < nRound; i += stride) {
-    const int route = i < b.n ? StageStepHead(tv, b, w.prestep, i, seed, geometry) : -1;
+    const int route = i < b.n ? StageLoopHead(tv, b, w.prestep, w.steppre, i, seed, geometry) : -1;
     RouteToQueues<5>(cc, route, static_cast<int32_t>(i), w.queue, w.count);
   }
+}
+
+// ---- the head of an e-/e+ step of the loop ------------------------------------------------------------------------------
+// StageStepHead (g4h_stages.cuh) + the geometry step + what G4HepEmTrackingManager::TrackElectron does around the pieces
+// (G4HepEmTrackingManager.cc:428-613): with fIsMultipleStepsInMSCTrans of the region (the reference's default) a step whose
+// length MSC limited goes on -- `continueStepping` -- with another HowFarToMSC / geometry / along-step / SampleMSC round over
+// what is left of the step limit of the discrete interaction (stepLimitLeft), as long as MSC keeps limiting it, geometry
+// does not and the track has energy; the mean losses of the rounds add up (totalEloss) and SampleLossFluctuations, the
+// discrete interaction and the scoring see the whole step.  One round = one iteration of the device loop: a track that
+// continues carries G4HB200_F_MSC_SUBSTEP and the caller's local variables (TrackGeo::sub_*) into the next iteration, where
+// this head resumes it: no new interaction lengths, no HowFarToDiscreteInteraction, the mean free paths of the first round.
+// prestep: energy at the beginning of this round (what SampleMSC reads); steppre: at the beginning of the step (what
+// SampleLossFluctuations reads; StageMSCSample hands it on in `prestep`).
+// A step of zero geometrical length follows G4HepEmElectronManager::Perform (.icc:461-470: nothing happens).
+template <class GeometryStep>
+G4H_FN int StageLoopHead(const TablesView& tv, const G4HB200ElectronBatch& b, double* prestep, double* steppre, int64_t i,
+                         uint64_t seed, const GeometryStep& geometry) {
+  const TrackGeo& geo = geometry.geo;
+  const Meta m   = LoadMeta(b.meta, i);
+  const Pair e   = LoadPair(b.ekin_logekin, i);
+  const Pair n01 = LoadPair(b.nia01, i);
+  const Pair n23 = LoadPair(b.nia23, i);
+  const Pair dzs = LoadPair(b.dirz_safety, i);
+  const Pair ir  = LoadPair(b.msc_irange_dynrf, i);
+  const Pair tg  = LoadPair(b.msc_tlimmin_gauss, i);
+  uint32_t f = static_cast<uint32_t>(m.flags);
+  ElectronState s;
+  s.ekin = e.a; s.logEkin = e.b;
+  s.imc = m.imc; s.id = m.id;
+  s.isPositron   = (f & G4HB200_F_POSITRON) != 0u;
+  s.onBoundary   = (f & G4HB200_F_ON_BOUNDARY) != 0u;
+  s.mscFirstStep = (f & G4HB200_F_MSC_FIRST_STEP) != 0u;
+  s.mscDisplace  = (f & G4HB200_F_MSC_DISPLACE) != 0u;
+  s.mscNoScatter = (f & G4HB200_F_MSC_NO_SCATTER) != 0u;
+  s.safety = dzs.b;
+  s.nIA[0] = n01.a; s.nIA[1] = n01.b; s.nIA[2] = n23.a; s.nIA[3] = n23.b;
+  s.initialRange = ir.a; s.dynRangeFactor = ir.b; s.tlimitMin = tg.a;
+  s.preStepEkin = 0.0; s.preStepLogEkin = 0.0;
+  bool hasGauss = (f & G4HB200_F_GAUSS_CACHED) != 0u;
+  double gauss  = tg.b;
+  DrawWindow dw;
+  dw.Init(seed, static_cast<uint32_t>(m.id), static_cast<uint32_t>(m.draw));
+  const bool resume = (f & G4HB200_F_MSC_SUBSTEP) != 0u;
+  int nXS = 0, iDProc = -1;
+  double lam, stepLimitLeft, totalEloss, stepPreEkin, stepPreLogEkin;
+  if (!resume) {
+    // .cc:430-445: interaction lengths, the discrete step limit, the winner MSC may replace, SavePreStepEKin
+    nXS = ResampleNumIALeftWindow(s.nIA, dw);
+    lam = HowFarToDiscreteInteractionILP(tv, s);
+    iDProc         = s.winner;
+    stepLimitLeft  = s.pStep;
+    totalEloss     = 0.0;
+    stepPreEkin    = s.ekin;
+    stepPreLogEkin = s.logEkin;
+  } else {
+    // .cc:574-596: what the previous round left
+    const Pair m01 = LoadPair(b.mfp01, i);
+    const Pair m23 = LoadPair(b.mfp23, i);
+    const Pair sl  = LoadPair(geo.sub_left_eloss, i);
+    const Pair sp  = LoadPair(geo.sub_pre, i);
+    const Pair sr  = LoadPair(geo.sub_range_proc, i);
+    s.mfp[0] = m01.a; s.mfp[1] = m01.b; s.mfp[2] = m23.a; s.mfp[3] = m23.b;
+    stepLimitLeft  = sl.a;
+    totalEloss     = sl.b;
+    stepPreEkin    = sp.a;
+    stepPreLogEkin = sp.b;
+    s.range  = sr.a;
+    iDProc   = static_cast<int>(sr.b);
+    s.pStep  = stepLimitLeft;
+    s.gStep  = stepLimitLeft;
+    s.winner = iDProc;
+    const double le = GetLogEKin(s);
+    lam = TransportMFP(tv.el[s.isPositron ? 1 : 0], G4H_LD(tv.mcImat + s.imc), s.ekin, le);
+  }
+  s.lambtr1 = MSCStepLimitApplies(s.pStep, s.ekin) ? lam : 0.0;
+  const double uA = nXS == 0 ? dw.u[0] : nXS == 1 ? dw.u[1] : nXS == 2 ? dw.u[2] : nXS == 3 ? dw.u[3] : dw.u[4];
+  const double uB = nXS == 0 ? dw.u[1] : nXS == 1 ? dw.u[2] : nXS == 2 ? dw.u[3] : nXS == 3 ? dw.u[4] : dw.Sixth();
+  const int nMSC = HowFarMSCCore(tv, s, hasGauss, gauss, uA, uB, dw.k0, dw.k1, static_cast<uint32_t>(m.draw + nXS));
+  const int callerFlags = static_cast<int>(G4H_LD(tv.regionPars + 8 * G4H_LD(tv.mcIreg + s.imc) + kRCallerFlags));
+  bool continueStepping = (callerFlags & 1) != 0 && s.winner == -2;  // .cc:427,450-453
+  geometry(i, s, dzs.a);
+  if (s.onBoundary) continueStepping = false;  // geometryLimitedStep (.cc:468-469)
+  const int how = AlongStepPhysics(tv, s);
+  if (how == kASStopped || how == kASMsc || how == kASNoMsc) totalEloss += s.edep;  // .cc:514
+  if (how == kASStopped || how == kASNoStep || how == kASZeroStep) continueStepping = false;
+  int route;
+  if (continueStepping) {
+    // .cc:574-596: the deposit is accumulated, the winner MSC replaced comes back, the rest of the step limit and of the range
+    stepLimitLeft -= s.pStep;
+    StorePair(geo.sub_left_eloss, i, stepLimitLeft, totalEloss);
+    StorePair(geo.sub_pre, i, stepPreEkin, stepPreLogEkin);
+    StorePair(geo.sub_range_proc, i, s.range - s.pStep, static_cast<double>(iDProc));
+    f |= G4HB200_F_MSC_SUBSTEP;
+    s.edep   = 0.0;
+    s.winner = iDProc;
+    route    = how == kASMsc ? (s.isPositron ? kQMscPos : kQMscEl) : -1;
+    StorePair(prestep, i, s.preStepEkin, s.preStepLogEkin);
+  } else {
+    f &= ~G4HB200_F_MSC_SUBSTEP;
+    if (how != kASNoStep) s.edep = totalEloss;  // .cc:600
+    route = AlongStepRoute(tv, s, how, stepPreEkin);
+    // the MSC stage reads the energy at the beginning of this round and leaves that of the step behind it
+    const bool toMsc = route == kQMscEl || route == kQMscPos;
+    StorePair(prestep, i, toMsc ? s.preStepEkin : stepPreEkin, toMsc ? s.preStepLogEkin : stepPreLogEkin);
+  }
+  StorePair(steppre, i, stepPreEkin, stepPreLogEkin);
+  f &= ~(G4HB200_F_ON_BOUNDARY | G4HB200_F_MSC_FIRST_STEP | G4HB200_F_MSC_ACTIVE | G4HB200_F_MSC_DISPLACE | G4HB200_F_MSC_NO_SCATTER |
+         G4HB200_F_GAUSS_CACHED);
+  if (s.onBoundary) f |= G4HB200_F_ON_BOUNDARY;
+  if (s.mscFirstStep) f |= G4HB200_F_MSC_FIRST_STEP;
+  if (s.mscActive) f |= G4HB200_F_MSC_ACTIVE;
+  if (s.mscDisplace) f |= G4HB200_F_MSC_DISPLACE;
+  if (s.mscNoScatter) f |= G4HB200_F_MSC_NO_SCATTER;
+  if (hasGauss) f |= G4HB200_F_GAUSS_CACHED;
+  StorePair(b.ekin_logekin, i, s.ekin, s.logEkin);
+  StorePair(b.nia01, i, s.nIA[0], s.nIA[1]);
+  StorePair(b.nia23, i, s.nIA[2], s.nIA[3]);
+  StorePair(b.msc_irange_dynrf, i, s.initialRange, s.dynRangeFactor);
+  StorePair(b.msc_tlimmin_gauss, i, s.tlimitMin, gauss);
+  StoreMeta(b.meta, i, Meta{m.imc, static_cast<int>(f), m.id, m.draw + nXS + nMSC});
+  StorePair(b.gstep_pstep, i, s.gStep, s.pStep);
+  StorePair(b.edep_dispx, i, s.edep, 0.0);  // fDisplacement = 0 (.icc:127-129)
+  StorePair(b.dispy_dispz, i, 0.0, 0.0);
+  b.winner[i] = s.winner;
+  StorePair(b.mfp01, i, s.mfp[0], s.mfp[1]);
+  StorePair(b.mfp23, i, s.mfp[2], s.mfp[3]);
+  StorePair(b.range_lambtr1, i, s.range, s.lambtr1);
+  StorePair(b.tstep_zpath, i, s.trueStep, s.zPath);
+  return route == -2 ? -1 : route;
 }
 
 // ---- the loop's steps as single persistent launches (g4h_fused.cuh) with the geometry step inside the head -------------
@@ -324,9 +458,9 @@ struct MakeSlabGammaGeometry {
 
 __global__ void __launch_bounds__(kThreadsPerBlock, G4H_MINB_FUSED)
 ShowerElectronFusedKernel(const __grid_constant__ TablesView tv, const __grid_constant__ G4HB200ElectronBatch b, double* prestep,
-                          const __grid_constant__ G4HB200SecondaryQueue sq, uint64_t seed, const __grid_constant__ SlabGeom g,
-                          const __grid_constant__ TrackGeo geo) {
-  ElFusedBody<false>(tv, b, prestep, sq, seed, MakeSlabGeometry{g, geo, b.dirx_diry});
+                          double* steppre, const __grid_constant__ G4HB200SecondaryQueue sq, uint64_t seed,
+                          const __grid_constant__ SlabGeom g, const __grid_constant__ TrackGeo geo) {
+  ElFusedBody<kHeadLoop>(tv, b, prestep, steppre, sq, seed, MakeSlabGeometry{g, geo, b.dirx_diry});
 }
 
 __global__ void __launch_bounds__(kThreadsPerBlock, G4H_MINB_FUSED)
@@ -458,7 +592,10 @@ ShowerElectronPostKernel(const __grid_constant__ SlabGeom g, const __grid_consta
       StorePair(geo.posx_posy, i, pos[0], pos[1]);
       StorePair(geo.posz_pad, i, pos[2], 0.0);
       if (alive) {
-        dzs.b = onBoundary ? 0.0 : SlabSafety(g, newVol, pos);
+        // between the MSC sub-steps of one step the caller does not update the safety (it is set once per step,
+        // G4HepEmTrackingManager.cc:419-423)
+        const bool subStep = (static_cast<uint32_t>(m.flags) & G4HB200_F_MSC_SUBSTEP) != 0u;
+        if (!subStep) dzs.b = onBoundary ? 0.0 : SlabSafety(g, newVol, pos);
         m.imc = imc;
         vol   = newVol;
       }
@@ -497,6 +634,16 @@ ShowerElectronPostKernel(const __grid_constant__ SlabGeom g, const __grid_consta
       StorePair(ngeo.posx_posy, o, pos[0], pos[1]);
       StorePair(ngeo.posz_pad, o, pos[2], 0.0);
       ngeo.vol[o] = vol;
+      if ((static_cast<uint32_t>(m.flags) & G4HB200_F_MSC_SUBSTEP) != 0u) {
+        // the step goes on in the next iteration: the mean free paths of its first round and the caller's local variables
+        const Pair m01 = LoadPair(b.mfp01, i), m23 = LoadPair(b.mfp23, i);
+        const Pair sl = LoadPair(geo.sub_left_eloss, i), sp = LoadPair(geo.sub_pre, i), sr = LoadPair(geo.sub_range_proc, i);
+        StorePair(nb.mfp01, o, m01.a, m01.b);
+        StorePair(nb.mfp23, o, m23.a, m23.b);
+        StorePair(ngeo.sub_left_eloss, o, sl.a, sl.b);
+        StorePair(ngeo.sub_pre, o, sp.a, sp.b);
+        StorePair(ngeo.sub_range_proc, o, sr.a, sr.b);
+      }
     }
   }
   hist.Flush(sc.hist, nbins);

@@ -144,6 +144,8 @@ typedef struct G4HB200Tables {
 #define G4HB200_F_MSC_NO_SCATTER 0x20u  /* fIsNoScatteringInMSC */
 #define G4HB200_F_GAUSS_CACHED 0x40u    /* G4HepEmRandomEngine::fIsGauss */
 #define G4HB200_F_WDT_ON 0x80u          /* gamma, stepping loop: under Woodcock tracking (isWDTOn of TrackGamma) */
+#define G4HB200_F_MSC_SUBSTEP 0x100u    /* e-/e+, stepping loop: between two MSC sub-steps of one step (continueStepping of
+                                           TrackElectron, G4HepEmTrackingManager.cc:447-597) */
 
 /* e-/e+ state: G4HepEmElectronTrack (G4HepEmRun/include/G4HepEmElectronTrack.hh:20-93) */
 typedef struct G4HB200ElectronBatch {

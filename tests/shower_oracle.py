@@ -270,6 +270,110 @@ def _woodcock(reference, slab, calo, couple_material, gm, gm_pos, dirs, seed, ma
     return on, phys, pos, vol, cut
 
 
+def _put(b, idx, sub):
+    for g in b.groups() + ("meta", "winner"):
+        getattr(b, g)[idx] = getattr(sub, g)
+
+
+def _op(reference, op, b, mask, seed, sec=None, flags=None):
+    """One track-level static of the reference (oracle/ref.py: electron_track_op) on the tracks of `b` selected by mask.
+    sec: secondaries are appended with parent indices of the full batch; returns the returned bools (full size) if flags."""
+    idx = np.flatnonzero(mask)
+    out = np.zeros(b.n, dtype=np.int32)
+    if len(idx) == 0:
+        return out
+    sub = _take(b, idx, batches.ElectronHostBatch)
+    fl = np.zeros(len(idx), dtype=np.int32) if flags else None
+    q = batches.SecondaryHostQueue(2 * len(idx)) if sec is not None else None
+    reference.electron_track_op(op, sub, seed, q, fl)
+    _put(b, idx, sub)
+    if fl is not None:
+        out[idx] = fl
+    if q is not None:
+        n = int(q.count[0])
+        k = int(sec.count[0])
+        sec.dirx_diry[k:k + n] = q.dirx_diry[:n]
+        sec.dirz_ekin[k:k + n] = q.dirz_ekin[:n]
+        sec.parent_kind[k:k + n] = q.parent_kind[:n]
+        sec.parent_slot[k:k + n, 0] = idx[q.parent_slot[:n, 0]]
+        sec.parent_slot[k:k + n, 1] = q.parent_slot[:n, 1]
+        sec.count[0] = k + n
+    return out
+
+
+F_MSC_SUBSTEP = 0x100
+
+
+def _electron_round(reference, slab, el, el_pos, el_vol, sub, multi, seed):
+    """One round of G4HepEmTrackingManager::TrackElectron (G4HepEmTrackingManager.cc:408-665) for every e-/e+ of the batch,
+    piece by piece through the reference's statics: a whole step, or -- where fIsMultipleStepsInMSCTrans of the region is set and
+    MSC limited the step -- one MSC sub-step of it (the track then carries F_MSC_SUBSTEP and the caller's local variables in `sub`
+    into the next round, like the device loop).  Returns (post-step positions, on-boundary mask, next volumes, secondaries)."""
+    n = el.n
+    everyone = np.ones(n, dtype=bool)
+    resume = (el.meta[:, 1] & F_MSC_SUBSTEP) != 0
+    fresh = ~resume
+    _op(reference, _capi.OP_RESAMPLE_NIA, el, fresh, seed)
+    _op(reference, _capi.OP_HOWFAR_DISCRETE, el, fresh, seed)
+    sub["proc"] = np.where(fresh, el.winner, sub["proc"]).astype(np.int32)
+    sub["left"] = np.where(fresh, el.gstep_pstep[:, 1], sub["left"])
+    sub["eloss"] = np.where(fresh, 0.0, sub["eloss"])
+    sub["pre_e"] = np.where(fresh, el.ekin_logekin[:, 0], sub["pre_e"])
+    sub["pre_le"] = np.where(fresh, el.ekin_logekin[:, 1], sub["pre_le"])
+    # a resumed step: the rest of the step limit, the reduced range, the winner MSC replaced (.cc:574-596)
+    el.gstep_pstep[resume, 0] = sub["left"][resume]
+    el.gstep_pstep[resume, 1] = sub["left"][resume]
+    el.range_lambtr1[resume, 0] = sub["range"][resume]
+    el.winner[resume] = sub["proc"][resume]
+    _op(reference, _capi.OP_HOWFAR_MSC, el, everyone, seed)
+    cont = multi[el.meta[:, 0]] & (el.winner == -2)
+    # geometry
+    dirs = np.stack([el.dirx_diry[:, 0], el.dirx_diry[:, 1], el.dirz_safety[:, 0]], axis=1)
+    dist, nv = slab.distance(el_vol, el_pos, dirs)
+    onb = dist < el.gstep_pstep[:, 0]
+    step = np.where(onb, dist, el.gstep_pstep[:, 0])
+    el_pos = el_pos + step[:, None] * dirs
+    el.gstep_pstep[:, 0] = step
+    el.meta[:, 1] = np.where(onb, el.meta[:, 1] | _capi.F_ON_BOUNDARY, el.meta[:, 1] & ~_capi.F_ON_BOUNDARY)
+    cont &= ~onb
+    # along the step
+    moving = step > 0.0
+    el.edep_dispx[:, 0] = 0.0
+    el.gstep_pstep[~moving, 1] = step[~moving]  # a step of zero length: G4HepEmElectronManager::Perform (.icc:461-470)
+    # SavePreStepEKin of this round (.cc:445,581): the logarithm is cached by HowFarToMSC
+    el.prestep[:, 0] = el.ekin_logekin[:, 0]
+    el.prestep[:, 1] = el.ekin_logekin[:, 1]
+    _op(reference, _capi.OP_UPDATE_PSTEP, el, moving, seed)
+    going = moving & (el.gstep_pstep[:, 1] > 0.0)
+    _op(reference, _capi.OP_UPDATE_NIA, el, going, seed)
+    stopped = _op(reference, _capi.OP_MEAN_ELOSS, el, going, seed, flags=True) != 0
+    sub["eloss"] = np.where(going, sub["eloss"] + el.edep_dispx[:, 0], sub["eloss"])
+    cont &= going & ~stopped
+    alive = going & ~stopped
+    _op(reference, _capi.OP_SAMPLE_MSC, el, alive, seed)
+    # between two sub-steps (.cc:574-596)
+    pstep = el.gstep_pstep[:, 1]
+    sub["left"] = np.where(cont, sub["left"] - pstep, sub["left"])
+    sub["range"] = np.where(cont, el.range_lambtr1[:, 0] - pstep, sub["range"])
+    el.edep_dispx[cont, 0] = 0.0
+    el.winner[cont] = sub["proc"][cont]
+    el.meta[:, 1] = np.where(cont, el.meta[:, 1] | F_MSC_SUBSTEP, el.meta[:, 1] & ~F_MSC_SUBSTEP)
+    # the end of the step (.cc:599-665)
+    done = moving & ~cont
+    el.edep_dispx[done, 0] = sub["eloss"][done]
+    fluct = alive & ~cont
+    el.prestep[fluct, 0] = sub["pre_e"][fluct]
+    el.prestep[fluct, 1] = sub["pre_le"][fluct]
+    stopped2 = _op(reference, _capi.OP_LOSS_FLUCT, el, fluct, seed, flags=True) != 0
+    sec = batches.SecondaryHostQueue(2 * n)
+    is_pos = (el.meta[:, 1] & _capi.F_POSITRON) != 0
+    _op(reference, _capi.OP_ANNIHILATE_AT_REST, el, is_pos & ((going & stopped) | (fluct & stopped2)), seed, sec=sec)
+    # PerformDiscrete returns at once without a winner or on a boundary; a step whose true length came out zero goes there too
+    discrete = (fluct & ~stopped2) | (moving & ~going)
+    _op(reference, _capi.OP_DISCRETE, el, discrete, seed, sec=sec)
+    return el_pos, onb, nv, sec
+
+
 ELECTRON_MASS_C2 = 5.1099890999999997e-01
 
 
@@ -286,6 +390,9 @@ def run(reference, calo, num_primaries, primary_ekin, seed, kind=_capi.SEC_ELECT
     (fused steps: the proposed step is accepted, nothing moves but by the MSC displacement), one scoring cell, a secondary
     inherits its parent's couple, no production cuts; calo is then the one-cell geometry of capi_shower.inl."""
     slab = Slab(calo)
+    multi = None
+    if tables is not None:
+        multi = ((tables.region_pars()[:, 7].astype(np.int64) & 1) != 0)[tables.couple_region()]
     if tables is not None:
         couple_cuts = tables.couple_cuts()
         apply_cuts = (tables.region_pars()[:, 7].astype(np.int64) & 2) != 0
@@ -315,6 +422,12 @@ def run(reference, calo, num_primaries, primary_ekin, seed, kind=_capi.SEC_ELECT
     gm_pos = np.zeros((gm.n, 3)); gm_pos[:, 0] = 0.0 if mixed is not None else slab.xfront
     el_vol = np.zeros(el.n, dtype=np.int32)
     gm_vol = np.zeros(gm.n, dtype=np.int32)
+
+    def new_sub(k):
+        return dict(left=np.zeros(k), eloss=np.zeros(k), pre_e=np.zeros(k), pre_le=np.zeros(k), range=np.zeros(k),
+                    proc=np.full(k, -1, dtype=np.int32))
+
+    el_sub = new_sub(el.n)
 
     def children(sec, parent_meta, parent_pos, parent_vol):
         r = sec  # raw queue order is irrelevant: everything is derived per record
@@ -369,13 +482,15 @@ def run(reference, calo, num_primaries, primary_ekin, seed, kind=_capi.SEC_ELECT
         stats["gamma_track_steps"] += gm.n
         stats["peak_electrons"] = max(stats["peak_electrons"], el.n)
         stats["peak_gammas"] = max(stats["peak_gammas"], gm.n)
-        next_el, next_gm = [], []
+        next_el, next_gm, next_sub = [], [], []
         # ---- e-/e+ ------------------------------------------------------------------------------------------------
         if el.n > 0 and mixed is not None:
             sec = batches.SecondaryHostQueue(2 * el.n)
             reference.electron_step(el, sec, seed, threads)
             onb = np.zeros(el.n, dtype=bool)
             nv = el_vol.copy()
+        elif el.n > 0 and multi is not None:
+            el_pos, onb, nv, sec = _electron_round(reference, slab, el, el_pos, el_vol, el_sub, multi, seed)
         elif el.n > 0:
             reference.electron_howfar(el, seed, threads)
             dirs = np.stack([el.dirx_diry[:, 0], el.dirx_diry[:, 1], el.dirz_safety[:, 0]], axis=1)
@@ -411,11 +526,13 @@ def run(reference, calo, num_primaries, primary_ekin, seed, kind=_capi.SEC_ELECT
             surv = _take(el, alive, batches.ElectronHostBatch)
             spos, svol = el_pos[alive], new_vol[alive].astype(np.int32)
             surv.meta[:, 0] = np.where(onb[alive], slab.couple[svol % slab.na], surv.meta[:, 0])
-            surv.dirz_safety[:, 1] = np.where(onb[alive], 0.0, slab.safety(svol, spos))
+            in_step = (surv.meta[:, 1] & F_MSC_SUBSTEP) != 0  # the caller sets the safety once per step (.cc:419-423)
+            surv.dirz_safety[:, 1] = np.where(in_step, surv.dirz_safety[:, 1], np.where(onb[alive], 0.0, slab.safety(svol, spos)))
             surv.edep_dispx[...] = 0.0
             surv.winner[...] = -1
             next_el += [(surv, spos, svol), (ce, cepos, cevol)]
             next_gm += [(cg, cgpos, cgvol)]
+            next_sub += [{k: v[alive] for k, v in el_sub.items()}, new_sub(ce.n)]
         # ---- gamma ------------------------------------------------------------------------------------------------------
         if gm.n > 0 and mixed is not None:
             sec = batches.SecondaryHostQueue(2 * gm.n)
@@ -473,9 +590,11 @@ def run(reference, calo, num_primaries, primary_ekin, seed, kind=_capi.SEC_ELECT
             surv.edep_pemxsec[:, 0] = 0.0
             next_el += [(ce, cepos, cevol)]
             next_gm += [(surv, spos, svol), (cg, cgpos, cgvol)]
+            next_sub += [new_sub(ce.n)]
         el = _concat([p[0] for p in next_el], batches.ElectronHostBatch)
         el_pos = np.concatenate([p[1] for p in next_el], axis=0) if next_el else np.zeros((0, 3))
         el_vol = np.concatenate([p[2] for p in next_el]).astype(np.int32) if next_el else np.zeros(0, dtype=np.int32)
+        el_sub = {k: np.concatenate([d[k] for d in next_sub]) for k in new_sub(0)} if next_sub else new_sub(0)
         gm = _concat([p[0] for p in next_gm], batches.GammaHostBatch)
         gm_pos = np.concatenate([p[1] for p in next_gm], axis=0) if next_gm else np.zeros((0, 3))
         gm_vol = np.concatenate([p[2] for p in next_gm]).astype(np.int32) if next_gm else np.zeros(0, dtype=np.int32)

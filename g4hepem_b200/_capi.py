@@ -172,6 +172,9 @@ class ShowerStats(C.Structure):
         ("leak_gamma", C.c_double),
         ("device_ms", C.c_double),
         ("kernel_launches", C.c_int64),
+        ("remaining_electrons", C.c_int64),
+        ("remaining_gammas", C.c_int64),
+        ("remaining_ekin", C.c_double),
     ]
 
 

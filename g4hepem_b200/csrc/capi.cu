@@ -817,9 +817,15 @@ int g4hb200_create(const G4HB200Tables* tables, int device, G4HB200** out) {
   G4HB200* h = new (std::nothrow) G4HB200;
   if (h == nullptr) return Fail(G4HB200_ENOMEM, "host allocation");
   h->device = device;
-  cudaDeviceProp prop;
-  G4H_CUDA(cudaGetDeviceProperties(&prop, device));
-  h->smCount = prop.multiProcessorCount;
+  {
+    int smCount = 0;
+    const cudaError_t err = cudaDeviceGetAttribute(&smCount, cudaDevAttrMultiProcessorCount, device);
+    if (err != cudaSuccess) {
+      delete h;
+      return Fail(G4HB200_ECUDA, "cudaDeviceGetAttribute", err);
+    }
+    h->smCount = smCount;
+  }
   h->desc = *tables;
   G4HB200Tables& d = h->desc;
   ArenaBuilder ab;
@@ -887,7 +893,14 @@ int g4hb200_create(const G4HB200Tables* tables, int device, G4HB200** out) {
       if (v >= 1 && v <= G4HB200::kNumSlots) h->splitParts = v;
     }
   }
-  G4H_CUDA(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+  {
+    const cudaError_t err = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
+    if (err != cudaSuccess) {
+      cudaFree(h->arena);
+      delete h;
+      return Fail(G4HB200_ECUDA, "cudaStreamCreateWithFlags", err);
+    }
+  }
   std::memset(&h->elDev, 0, sizeof(h->elDev));
   std::memset(&h->gmDev, 0, sizeof(h->gmDev));
   std::memset(&h->secDev, 0, sizeof(h->secDev));
@@ -898,6 +911,14 @@ int g4hb200_create(const G4HB200Tables* tables, int device, G4HB200** out) {
 int g4hb200_destroy(G4HB200* h) {
   if (h == nullptr) return 0;
   cudaSetDevice(h->device);
+  cudaDeviceSynchronize();
+  // per-kernel timing rows nobody collected (g4hb200_kernel_times)
+  for (auto& tc : h->timed) {
+    for (auto& e : tc.ev) cudaEventDestroy(e);
+    cudaEventDestroy(tc.done);
+    if (tc.counts != nullptr) cudaFreeHost(tc.counts);
+  }
+  h->timed.clear();
   if (h->elCap > 0) g4hb200_electron_batch_free(h, &h->elDev);
   if (h->gmCap > 0) g4hb200_gamma_batch_free(h, &h->gmDev);
   if (h->secCap > 0) g4hb200_secondary_queue_free(h, &h->secDev);

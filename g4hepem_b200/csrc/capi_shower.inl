@@ -206,8 +206,9 @@ int RunStepLoop(G4HB200* h, const G4HB200SlabGeometry* geom, int64_t numPrimarie
   }
   ++h->launches;
   int status = 0;
+  const int stepLimit = maxSteps > 0 ? maxSteps : 1000000;
   for (int step = 0; (nEl > 0 || nGm > 0); ++step) {
-    if (maxSteps > 0 && step >= maxSteps) break;
+    if (step >= stepLimit) break;
     const int nxt = cur ^ 1;
     stats->num_steps += 1;
     stats->electron_track_steps += nEl;
@@ -286,10 +287,32 @@ int RunStepLoop(G4HB200* h, const G4HB200SlabGeometry* geom, int64_t numPrimarie
   }
   cudaEventRecord(ev1, st);
   cudaEventSynchronize(ev1);
+  // whatever was forked onto the gamma stream and the part-batch streams is done before the stores go away (an error
+  // path leaves the loop between a fork and its join)
+  cudaStreamSynchronize(sg);
+  for (auto& slot : h->slots) {
+    if (slot.stream != nullptr) cudaStreamSynchronize(slot.stream);
+    for (auto& a : slot.aux) if (a != nullptr) cudaStreamSynchronize(a);
+  }
+  if (h->gmSlot2.stream != nullptr) cudaStreamSynchronize(h->gmSlot2.stream);
   float ms = 0.f;
   cudaEventElapsedTime(&ms, ev0, ev1);
   stats->device_ms = ms;
   stats->kernel_launches = h->launches - launches0;
+  if (status == 0 && (nEl > 0 || nGm > 0)) {
+    // stopped on max_steps: what is left alive
+    stats->remaining_electrons = nEl;
+    stats->remaining_gammas    = nGm;
+    std::vector<double> e(static_cast<size_t>(2 * (nEl > nGm ? nEl : nGm)));
+    double left = 0.0;
+    if (nEl > 0 && cudaMemcpy(e.data(), s.el[cur].ekin_logekin, static_cast<size_t>(nEl) * 16, cudaMemcpyDeviceToHost) == cudaSuccess) {
+      for (int64_t k = 0; k < nEl; ++k) left += e[2 * k];
+    }
+    if (nGm > 0 && cudaMemcpy(e.data(), s.gm[cur].ekin_logekin, static_cast<size_t>(nGm) * 16, cudaMemcpyDeviceToHost) == cudaSuccess) {
+      for (int64_t k = 0; k < nGm; ++k) left += e[2 * k];
+    }
+    stats->remaining_ekin = left;
+  }
   if (status == 0) {
     double leak[2];
     cudaMemcpy(edepOut, s.score.hist, static_cast<size_t>(nbins) * 8, cudaMemcpyDeviceToHost);

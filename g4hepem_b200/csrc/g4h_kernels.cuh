@@ -10,6 +10,7 @@
 #include <cuda_runtime.h>
 
 #include "g4h_batch_io.cuh"
+#include "g4h_tma.cuh"
 
 namespace g4h {
 
@@ -138,7 +139,7 @@ ElectronLookupsKernel(const __grid_constant__ TablesView tv, int64_t n, const in
 }
 
 // the same with the particle's hot tables (loss, restricted cross sections, nuclear, transport: one contiguous block
-// of the arena) staged in shared memory: a look-up gathers 8 B from up to 32 different 32 B sectors of L1 per
+// of the arena) staged in shared memory by a TMA bulk copy (g4h_tma.cuh): a look-up gathers 8 B from up to 32 different 32 B sectors of L1 per
 // instruction; shared memory serves scattered 8 B words at bank rate
 // the shared-memory copy of *p: the address is derived from the shared array, not from the global pointer (the
 // compiler picks the load instruction from the provenance of the address)
@@ -155,8 +156,9 @@ ElectronLookupsSmemKernel(const __grid_constant__ TablesView tv, int64_t n, cons
   const char* lo = reinterpret_cast<const char*>(ed.lossEGrid);
   const char* hi = reinterpret_cast<const char*>(ed.tr1Data + 2 * ed.numLoss * tv.numMat);
   const int n16  = static_cast<int>((hi - lo + 15) / 16);
-  for (int k = threadIdx.x; k < n16; k += blockDim.x) smemTables[k] = __ldg(reinterpret_cast<const double2*>(lo) + k);
-  __syncthreads();
+  // the block travels through the TMA unit (one cp.async.bulk issued by one thread, an mbarrier counts the bytes in)
+  __shared__ uint64_t tablesArrived;
+  StageThroughTma(smemTables, lo, static_cast<uint32_t>(n16) * 16u, &tablesArrived);
   ElectronTablesView es = ed;
   es.lossEGrid = StagedPtr(smemTables, lo, ed.lossEGrid);
   es.lossData  = StagedPtr(smemTables, lo, ed.lossData);

@@ -377,11 +377,22 @@ typedef struct G4HB200ShowerStats {
   double leak_electron, leak_gamma; /* kinetic energy [MeV] that left the calorimeter */
   double device_ms;             /* CUDA-event time of the whole loop on the handle's stream */
   int64_t kernel_launches;
+  /* what was still alive when the loop stopped on max_steps (all zero for a loop that ran to the end): the deposits and
+   * the leakage are then incomplete by that much kinetic energy */
+  int64_t remaining_electrons, remaining_gammas;
+  double remaining_ekin;        /* MeV */
 } G4HB200ShowerStats;
 
 /* primary_kind: G4HB200_SEC_ELECTRON / _POSITRON / _GAMMA.  first_track_id: id of the first primary (ids are consecutive:
  * give every rank its own range).  capacity: tracks per store (e-/e+ and gamma each); G4HB200_ECAPACITY if exceeded.
- * edep_out: host array [num_layers * num_absorbers], MeV. */
+ * max_steps: 0 = until no track is left (at most 1 000 000 iterations: G4HB200_ECUDA-free safety net against a track that
+ * never ends); > 0: stop after that many iterations and report what is left in stats->remaining_*.
+ * edep_out: host array [num_layers * num_absorbers], MeV.
+ * Streams of secondaries: a secondary's (track id, first draw) is a Philox hash of (parent id, parent draw counter, slot):
+ * 32 + 29 random bits.  Ids are NOT guaranteed unique: among N tracks about N^2 / 2^33 pairs share an id, and two
+ * tracks with the same id consume overlapping stretches of one stream only if their first draws lie within their
+ * lifetimes' draws of each other (~1e3 of 2^29) -- for the 1e8 tracks of 4096 x 10 GeV showers that is a few pairs of
+ * tracks in 1e8, each sharing a few hundred uniforms.  The deposits do not depend on batching or sharding either way. */
 int g4hb200_shower_run(G4HB200* h, const G4HB200SlabGeometry* geom, int64_t num_primaries, int32_t primary_kind,
                        double primary_ekin, uint64_t seed, int32_t first_track_id, int64_t capacity, int32_t max_steps,
                        double* edep_out, G4HB200ShowerStats* stats);

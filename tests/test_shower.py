@@ -165,3 +165,18 @@ def test_mixed_run_matches_cpu_driver_step_by_step(engine, reference, flat_table
         for k in ("num_steps", "electron_track_steps", "gamma_track_steps", "secondaries", "peak_electrons", "peak_gammas"):
             assert got[k] == want[k], (steps, k, got[k], want[k])
         assert abs(got_e - want_e) <= 1e-9 * want_e, (steps, got_e, want_e)
+
+
+@pytest.mark.gpu
+def test_loop_stopped_on_max_steps_reports_what_is_left(engine):
+    """A loop that stops on max_steps says so: the populations and the kinetic energy still alive are in the stats, and the
+    energy balance closes with them (up to 2 m_e c^2 per e+ created so far)."""
+    calo = shower.SlabCalorimeter()
+    res = shower.run(engine, calo, 16, 500.0, SEED, max_steps=12, capacity=1 << 16)
+    st = res.stats
+    assert st["num_steps"] == 12
+    assert st["remaining_electrons"] > 0 and st["remaining_gammas"] > 0 and st["remaining_ekin"] > 0.0
+    total = res.edep.sum() + st["leak_electron"] + st["leak_gamma"] + st["remaining_ekin"]
+    assert abs(total - 16 * 500.0) < 2 * 0.51099891 * st["secondaries"] + 1e-6
+    done = shower.run(engine, calo, 16, 500.0, SEED, capacity=1 << 16)
+    assert done.stats["remaining_electrons"] == 0 and done.stats["remaining_gammas"] == 0 and done.stats["remaining_ekin"] == 0.0

@@ -136,6 +136,10 @@ struct G4HB200 {
   // instructions for the head), while the pipeline runs six samplers side by side and overlaps stages of two half batches.
   // It stays available for A/B runs: G4HB200_FUSED=1 (always), G4HB200_FUSED_BELOW=n (below n tracks).
   int64_t fusedBelow = 0;
+  // the stepping loop runs as CUDA graphs with the populations on the device once both populations are below tailBelow
+  // tracks (capi_shower.inl: RunGraphTail); G4HB200_GRAPH_TAIL=0 turns it off, G4HB200_TAIL_BELOW=n moves the threshold
+  bool graphTail = true;
+  int64_t tailBelow = 1 << 20;
   bool Fused(int64_t n) const { return n < fusedBelow; }
   // device batches of at least this many tracks run as two half-batch pipelines side by side (G4HB200_SPLIT_MIN)
   int64_t splitThreshold = 1 << 18;
@@ -887,6 +891,11 @@ int g4hb200_create(const G4HB200Tables* tables, int device, G4HB200** out) {
   {
     if (const char* fu = std::getenv("G4HB200_FUSED")) h->fusedBelow = fu[0] != '0' ? (int64_t{1} << 62) : 0;
     if (const char* fb = std::getenv("G4HB200_FUSED_BELOW")) h->fusedBelow = std::atoll(fb);
+    if (const char* gt = std::getenv("G4HB200_GRAPH_TAIL")) h->graphTail = gt[0] != '0';
+    if (const char* tb = std::getenv("G4HB200_TAIL_BELOW")) {
+      const long long v = std::atoll(tb);
+      if (v >= 256) h->tailBelow = v;
+    }
     if (const char* sp = std::getenv("G4HB200_SPLIT_MIN")) h->splitThreshold = std::atoll(sp);
     if (const char* sp = std::getenv("G4HB200_SPLIT_PARTS")) {
       const int v = std::atoi(sp);

@@ -10,6 +10,8 @@ struct ShowerStore {
   void* geoMem = nullptr;
   void* scoreMem = nullptr;
   ShowerScore score;
+  ShowerCtrl* ctrl = nullptr;       // device bookkeeping of the graph-driven tail (inside scoreMem)
+  ShowerCtrl* pinnedCtrl = nullptr; // host copy
   int32_t* pinned = nullptr;  // {next e-, next gamma, overflow, secondaries e-, secondaries gamma}
 };
 
@@ -32,6 +34,7 @@ int CarveGeo(unsigned char*& p, int64_t cap, TrackGeo& g, bool withSubSteps) {
   p += cap * 4;
   g.nextVol = reinterpret_cast<int32_t*>(p);
   p += cap * 4;
+  g.n_dev = nullptr;
   return 0;
 }
 
@@ -45,6 +48,7 @@ void FreeShowerStore(G4HB200* h, ShowerStore& s) {
   if (s.geoMem != nullptr) cudaFree(s.geoMem);
   if (s.scoreMem != nullptr) cudaFree(s.scoreMem);
   if (s.pinned != nullptr) cudaFreeHost(s.pinned);
+  if (s.pinnedCtrl != nullptr) cudaFreeHost(s.pinnedCtrl);
 }
 
 }  // namespace
@@ -92,6 +96,110 @@ extern "C" int g4hb200_mixed_run(G4HB200* h, int64_t numElectrons, int64_t numGa
 }
 
 namespace {
+// One iteration of the loop with the populations on the device (cur -> the other store), enqueued on st / sg: what the
+// body of RunStepLoop's loop does, for stream capture.
+int EnqueueTailIteration(G4HB200* h, const SlabGeom& g, ShowerStore& s, uint64_t seed, int cur, cudaStream_t st, cudaStream_t sg) {
+  const int nxt = cur ^ 1;
+  // sizes the grids (a full wave: the populations may still grow); the kernels read the live counts from ShowerCtrl
+  const int64_t nMax = s.score.capacity;
+  int rc = 0;
+  ShowerIterKernel<<<1, 32, 0, st>>>(s.ctrl, s.score.nextCount, s.secEl.count, s.secGm.count, s.score.overflow);
+  ++h->launches;
+  G4H_CUDA(cudaEventRecord(h->loopFork, st));
+  G4H_CUDA(cudaStreamWaitEvent(sg, h->loopFork, 0));
+  {
+    G4HB200ElectronBatch b = s.el[cur];
+    b.n = nMax;
+    TrackGeo geo = s.elGeo[cur];
+    geo.n_dev = &s.ctrl->cur[0];
+    const SlabHead slab{g, geo};
+    if ((rc = LaunchElectronPipeline<true>(h, &b, &s.secEl, seed, st, 0, &slab)) != 0) return rc;
+    ShowerElectronPostKernel<<<OneWave(h, ShowerElectronPostKernel, nMax), kThreadsPerBlock, 0, st>>>(g, b, geo, s.el[nxt], s.elGeo[nxt],
+                                                                                                  s.score);
+    ShowerSecondaryKernel<<<OneWave(h, ShowerSecondaryKernel, 2 * nMax), kThreadsPerBlock, 0, st>>>(
+        h->view, g, seed, s.secEl, s.el[cur].meta, s.elGeo[cur], s.el[nxt], s.elGeo[nxt], s.gm[nxt], s.gmGeo[nxt], s.score);
+    h->launches += 2;
+  }
+  {
+    G4HB200GammaBatch b = s.gm[cur];
+    b.n = nMax;
+    TrackGeo geo = s.gmGeo[cur];
+    geo.n_dev = &s.ctrl->cur[1];
+    const SlabHead slab{g, geo};
+    if ((rc = LaunchGammaPipeline<2>(h, &b, &s.secGm, seed, sg, false, &slab)) != 0) return rc;
+    ShowerGammaPostKernel<<<OneWave(h, ShowerGammaPostKernel, nMax), kThreadsPerBlock, 0, sg>>>(g, b, geo, s.gm[nxt], s.gmGeo[nxt], s.score);
+    ShowerSecondaryKernel<<<OneWave(h, ShowerSecondaryKernel, 2 * nMax), kThreadsPerBlock, 0, sg>>>(
+        h->view, g, seed, s.secGm, s.gm[cur].meta, s.gmGeo[cur], s.el[nxt], s.elGeo[nxt], s.gm[nxt], s.gmGeo[nxt], s.score);
+    h->launches += 2;
+  }
+  G4H_CUDA(cudaEventRecord(h->loopJoin, sg));
+  G4H_CUDA(cudaStreamWaitEvent(st, h->loopJoin, 0));
+  return 0;
+}
+
+// The rest of the loop from store `cur` on: graphs of two iterations (cur -> other -> cur), polled every kTailPoll launches.
+int RunGraphTail(G4HB200* h, const SlabGeom& g, ShowerStore& s, uint64_t seed, int cur, cudaStream_t st, cudaStream_t sg,
+                 G4HB200ShowerStats* stats) {
+  constexpr int kTailPoll = 4;
+  // the counters of the last host-driven iteration have been booked by the host: the tail's bookkeeping starts from zero
+  G4H_CUDA(cudaMemsetAsync(s.secEl.count, 0, sizeof(int32_t), st));
+  G4H_CUDA(cudaMemsetAsync(s.secGm.count, 0, sizeof(int32_t), st));
+  G4H_CUDA(cudaMemsetAsync(s.ctrl, 0, sizeof(ShowerCtrl), st));
+  G4H_CUDA(cudaStreamSynchronize(st));
+  const int64_t launchesBefore = h->launches;
+  cudaGraph_t graph = nullptr;
+  cudaGraphExec_t exec = nullptr;
+  G4H_CUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+  int rc = EnqueueTailIteration(h, g, s, seed, cur, st, sg);
+  if (rc == 0) rc = EnqueueTailIteration(h, g, s, seed, cur ^ 1, st, sg);
+  const cudaError_t endErr = cudaStreamEndCapture(st, &graph);
+  if (rc != 0 || endErr != cudaSuccess || graph == nullptr) {
+    if (graph != nullptr) cudaGraphDestroy(graph);
+    return rc != 0 ? rc : Fail(G4HB200_ECUDA, "cudaStreamEndCapture", endErr);
+  }
+  const int64_t launchesPerGraph = h->launches - launchesBefore;
+  h->launches = launchesBefore;
+  cudaError_t err = cudaGraphInstantiate(&exec, graph, 0);
+  cudaGraphDestroy(graph);
+  if (err != cudaSuccess) return Fail(G4HB200_ECUDA, "cudaGraphInstantiate", err);
+  int status = 0;
+  for (int poll = 0; poll < 250000; ++poll) {
+    for (int k = 0; k < kTailPoll; ++k) {
+      if ((err = cudaGraphLaunch(exec, st)) != cudaSuccess) break;
+      h->launches += launchesPerGraph;
+    }
+    if (err != cudaSuccess) {
+      status = Fail(G4HB200_ECUDA, "cudaGraphLaunch", err);
+      break;
+    }
+    cudaMemcpyAsync(s.pinned, s.score.nextCount, 3 * sizeof(int32_t), cudaMemcpyDeviceToHost, st);
+    if ((err = cudaStreamSynchronize(st)) != cudaSuccess) {
+      status = Fail(G4HB200_ECUDA, "shower tail", err);
+      break;
+    }
+    if (s.pinned[2] != 0) {
+      status = Fail(G4HB200_ECAPACITY, "shower track store capacity exceeded");
+      break;
+    }
+    if (s.pinned[0] == 0 && s.pinned[1] == 0) break;
+  }
+  cudaGraphExecDestroy(exec);
+  if (status != 0) return status;
+  int32_t lastSec[2] = {0, 0};
+  G4H_CUDA(cudaMemcpyAsync(s.pinnedCtrl, s.ctrl, sizeof(ShowerCtrl), cudaMemcpyDeviceToHost, st));
+  G4H_CUDA(cudaMemcpyAsync(&lastSec[0], s.secEl.count, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+  G4H_CUDA(cudaMemcpyAsync(&lastSec[1], s.secGm.count, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+  G4H_CUDA(cudaStreamSynchronize(st));
+  const ShowerCtrl& c = *s.pinnedCtrl;
+  stats->num_steps += c.steps;
+  stats->electron_track_steps += c.sumEl;
+  stats->gamma_track_steps += c.sumGm;
+  stats->secondaries += c.sumSec + lastSec[0] + lastSec[1];
+  if (c.peakEl > stats->peak_electrons) stats->peak_electrons = c.peakEl;
+  if (c.peakGm > stats->peak_gammas) stats->peak_gammas = c.peakGm;
+  return 0;
+}
+
 int RunStepLoop(G4HB200* h, const G4HB200SlabGeometry* geom, int64_t numPrimaries, int32_t primaryKind, double primaryEkin,
                 uint64_t seed, int32_t firstTrackId, int64_t capacity, int32_t maxSteps, double* edepOut,
                 G4HB200ShowerStats* stats, const MixedSpec& mixed) {
@@ -151,7 +259,7 @@ int RunStepLoop(G4HB200* h, const G4HB200SlabGeometry* geom, int64_t numPrimarie
     CarveGeo(p, capacity, s.elGeo[1], true);
     CarveGeo(p, capacity, s.gmGeo[0], false);
     CarveGeo(p, capacity, s.gmGeo[1], false);
-    const size_t sbytes = static_cast<size_t>(nbins) * 8 + 2 * 8 + 4 * 4;
+    const size_t sbytes = static_cast<size_t>(nbins) * 8 + 2 * 8 + 4 * 4 + sizeof(ShowerCtrl);
     if (cudaMalloc(&s.scoreMem, sbytes) != cudaSuccess) return fail(Fail(G4HB200_ENOMEM, "cudaMalloc(shower score)"));
     unsigned char* q = static_cast<unsigned char*>(s.scoreMem);
     s.score.hist = reinterpret_cast<double*>(q);
@@ -159,8 +267,10 @@ int RunStepLoop(G4HB200* h, const G4HB200SlabGeometry* geom, int64_t numPrimarie
     s.score.nextCount = reinterpret_cast<int32_t*>(s.score.leak + 2);
     s.score.overflow = s.score.nextCount + 2;
     s.score.capacity = capacity;
+    s.ctrl = reinterpret_cast<ShowerCtrl*>(s.score.nextCount + 4);  // 8-byte aligned: nbins * 8 + 16 + 16
     if (cudaMemset(s.scoreMem, 0, sbytes) != cudaSuccess) return fail(Fail(G4HB200_ECUDA, "cudaMemset(score)"));
-    if (cudaMallocHost(reinterpret_cast<void**>(&s.pinned), 8 * sizeof(int32_t)) != cudaSuccess)
+    if (cudaMallocHost(reinterpret_cast<void**>(&s.pinned), 8 * sizeof(int32_t)) != cudaSuccess ||
+        cudaMallocHost(reinterpret_cast<void**>(&s.pinnedCtrl), sizeof(ShowerCtrl)) != cudaSuccess)
       return fail(Fail(G4HB200_ENOMEM, "cudaMallocHost"));
   }
   // size the pipelines' workspaces once (they grow on demand otherwise: a reallocation per iteration while the
@@ -209,6 +319,17 @@ int RunStepLoop(G4HB200* h, const G4HB200SlabGeometry* geom, int64_t numPrimarie
   const int stepLimit = maxSteps > 0 ? maxSteps : 1000000;
   for (int step = 0; (nEl > 0 || nGm > 0); ++step) {
     if (step >= stepLimit) break;
+    // Most iterations of a shower step a few thousand tracks: a chain of ~25 small kernels whose ~100 API calls and one
+    // host synchronisation cost more than the kernels run.  Below tailBelow tracks per population (from the second
+    // iteration on: the first one creates the streams and sizes the launches) the loop therefore runs as CUDA graphs of
+    // two iterations each with the populations on the device (ShowerCtrl, TrackGeo::n_dev), full-wave grids -- the
+    // populations may still grow -- and the host looks at the counters once per kTailPoll graph launches.  Above it the
+    // host-driven iteration with its two half-batch pipelines side by side is the faster one.
+    if (step > 0 && maxSteps == 0 && !mixed.enabled && h->graphTail && !h->timing && nEl < h->tailBelow && nGm < h->tailBelow) {
+      status = RunGraphTail(h, g, s, seed, cur, st, sg, stats);
+      nEl = nGm = 0;
+      break;
+    }
     const int nxt = cur ^ 1;
     stats->num_steps += 1;
     stats->electron_track_steps += nEl;

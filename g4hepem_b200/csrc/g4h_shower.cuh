@@ -52,6 +52,16 @@ struct TrackGeo {
   double* sub_left_eloss;  // pairs {stepLimitLeft, totalEloss}
   double* sub_pre;         // pairs {preStepEkin, preStepLogEkin} of the whole step
   double* sub_range_proc;  // pairs {range left after the sub-steps so far, iDProc (the discrete winner MSC replaced)}
+  // number of live tracks of the store where the host does not know it (the graph-driven tail of the loop, capi_shower.inl);
+  // NULL: the batch's n
+  const int32_t* n_dev;
+};
+
+// device-side bookkeeping of the graph-driven tail of the loop: what the host keeps in local variables otherwise
+struct ShowerCtrl {
+  int32_t cur[2];  // populations of the running iteration {e-/e+, gamma}
+  int32_t pad[2];
+  long long steps, sumEl, sumGm, sumSec, peakEl, peakGm;
 };
 
 struct ShowerScore {
@@ -287,12 +297,13 @@ ShowerGammaHeadKernel(const __grid_constant__ TablesView tv, const __grid_consta
                       const __grid_constant__ ElectronWork w, uint64_t seed, const __grid_constant__ SlabGeom g,
                       const __grid_constant__ TrackGeo geo) {
   const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
-  const int64_t nRound = RoundUpToCta(b.n);
+  const int64_t n      = geo.n_dev != nullptr ? *geo.n_dev : b.n;
+  const int64_t nRound = RoundUpToCta(n);
   __shared__ CtaCounters<3> cc;
   cc.Init();
   const SlabGammaGeometryStep geometry{g, geo};
   for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < nRound; i += stride) {
-    const int route = i < b.n ? StageGammaHead<2>(tv, b, i, seed, geometry) : -1;
+    const int route = i < n ? StageGammaHead<2>(tv, b, i, seed, geometry) : -1;
     RouteToQueues<3>(cc, route, static_cast<int32_t>(i), w.queue, w.count);
   }
 }
@@ -304,12 +315,13 @@ ShowerElectronHeadKernel(const __grid_constant__ TablesView tv, const __grid_con
                          const __grid_constant__ ElectronWork w, uint64_t seed, const __grid_constant__ SlabGeom g,
                          const __grid_constant__ TrackGeo geo) {
   const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
-  const int64_t nRound = RoundUpToCta(b.n);
+  const int64_t n      = geo.n_dev != nullptr ? *geo.n_dev : b.n;
+  const int64_t nRound = RoundUpToCta(n);
   __shared__ CtaCounters<5> cc;
   cc.Init();
   const SlabGeometryStep geometry{g, geo, b.dirx_diry};
   for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < nRound; i += stride) {
-    const int route = i < b.n ? StageLoopHead(tv, b, w.prestep, w.steppre, i, seed, geometry) : -1;
+    const int route = i < n ? StageLoopHead(tv, b, w.prestep, w.steppre, i, seed, geometry) : -1;
     RouteToQueues<5>(cc, route, static_cast<int32_t>(i), w.queue, w.count);
   }
 }
@@ -535,14 +547,15 @@ ShowerElectronPostKernel(const __grid_constant__ SlabGeom g, const __grid_consta
   if (threadIdx.x == 0) sLeak = 0.0;
   __syncthreads();
   const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
-  const int64_t nRound = RoundUpToCta(b.n);
+  const int64_t nLive  = geo.n_dev != nullptr ? *geo.n_dev : b.n;
+  const int64_t nRound = RoundUpToCta(nLive);
   for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < nRound; i += stride) {
     bool alive = false;
     Meta m{0, 0, 0, 0};
     Pair e{0, 0}, dxy{0, 0}, dzs{0, 0};
     double pos[3] = {0, 0, 0};
     int vol = -1;
-    if (i < b.n) {
+    if (i < nLive) {
       m   = LoadMeta(b.meta, i);
       e   = LoadPair(b.ekin_logekin, i);
       dxy = LoadPair(b.dirx_diry, i);
@@ -664,13 +677,14 @@ ShowerGammaPostKernel(const __grid_constant__ SlabGeom g, const __grid_constant_
   if (threadIdx.x == 0) sLeak = 0.0;
   __syncthreads();
   const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
-  const int64_t nRound = RoundUpToCta(b.n);
+  const int64_t nLive  = geo.n_dev != nullptr ? *geo.n_dev : b.n;
+  const int64_t nRound = RoundUpToCta(nLive);
   for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < nRound; i += stride) {
     bool alive = false;
     Meta m{0, 0, 0, 0};
     Pair e{0, 0}, dxy{0, 0}, dzn{0, 0}, pxy{0, 0}, pz{0, 0};
     int vol = -1;
-    if (i < b.n) {
+    if (i < nLive) {
       m   = LoadMeta(b.meta, i);
       e   = LoadPair(b.ekin_logekin, i);
       dxy = LoadPair(b.dirx_diry, i);
@@ -850,6 +864,30 @@ ShowerSecondaryKernel(const __grid_constant__ TablesView tv, const __grid_consta
     }
   }
   if (g.inheritCouple == 0) hist.Flush(sc.hist, nbins);
+}
+
+// ---- the top of an iteration of the graph-driven tail: what the host does between two iterations otherwise --------------------
+// (populations of the iteration <- what the previous one left in the next-step stores; counters back to zero; statistics)
+__global__ void ShowerIterKernel(ShowerCtrl* ctrl, int32_t* nextCount, int32_t* secElCount, int32_t* secGmCount,
+                                 const int32_t* overflow) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  ctrl->sumSec += static_cast<long long>(*secElCount) + *secGmCount;  // secondaries the previous iteration created
+  // a store that ran out of capacity ends the run (the host reports it at its next look): nothing more is stepped
+  const bool dead = *overflow != 0;
+  const int nEl = dead ? 0 : nextCount[0], nGm = dead ? 0 : nextCount[1];
+  ctrl->cur[0]  = nEl;
+  ctrl->cur[1]  = nGm;
+  nextCount[0]  = 0;
+  nextCount[1]  = 0;
+  *secElCount   = 0;
+  *secGmCount   = 0;
+  if (nEl > 0 || nGm > 0) {
+    ctrl->steps += 1;
+    ctrl->sumEl += nEl;
+    ctrl->sumGm += nGm;
+    if (nEl > ctrl->peakEl) ctrl->peakEl = nEl;
+    if (nGm > ctrl->peakGm) ctrl->peakGm = nGm;
+  }
 }
 
 // primaries: at the front face of the calorimeter, along +x, entering (on the boundary)

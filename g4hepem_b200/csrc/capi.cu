@@ -10,6 +10,7 @@
 #include <new>
 #include <string>
 #include <unordered_map>
+#include <unordered_set>
 #include <vector>
 
 #include "../../include/g4hepem_b200.h"
@@ -158,6 +159,22 @@ struct G4HB200 {
   };
   std::vector<TimedCall> timed;
   std::unordered_map<const void*, int> residentCtas;  // per kernel: CTAs of kThreadsPerBlock threads that fit on one SM
+  // The table arena (< 1 MB) as a persisting L2 access-policy window on every stream the library launches on: track state
+  // streams through L2 at hundreds of MB per step, the tables must not be evicted by it.  G4HB200_L2_PERSIST=0 turns it off.
+  bool l2Persist = false;
+  std::unordered_set<cudaStream_t> pinnedStreams;
+  void PinTables(cudaStream_t st) {
+    if (!l2Persist || st == nullptr || pinnedStreams.count(st) != 0) return;
+    cudaStreamAttrValue attr;
+    std::memset(&attr, 0, sizeof(attr));
+    attr.accessPolicyWindow.base_ptr  = arena;
+    attr.accessPolicyWindow.num_bytes = arenaBytes;
+    attr.accessPolicyWindow.hitRatio  = 1.0f;
+    attr.accessPolicyWindow.hitProp   = cudaAccessPropertyPersisting;
+    attr.accessPolicyWindow.missProp  = cudaAccessPropertyStreaming;
+    if (cudaStreamSetAttribute(st, cudaStreamAttributeAccessPolicyWindow, &attr) != cudaSuccess) cudaGetLastError();
+    pinnedStreams.insert(st);
+  }
 };
 
 namespace {
@@ -268,6 +285,7 @@ int LaunchGammaHowFar(G4HB200* h, G4HB200GammaBatch* dev, uint64_t seed, void* s
   if (rc != 0) return rc;
   if (dev == nullptr || dev->n < 0) return Fail(G4HB200_EINVAL, "bad gamma batch");
   if (dev->n == 0) return 0;
+  h->PinTables(static_cast<cudaStream_t>(stream));
   GammaHowFarKernel<<<OneWave(h, GammaHowFarKernel, dev->n), kThreadsPerBlock, 0, static_cast<cudaStream_t>(stream)>>>(h->view, *dev, seed);
   ++h->launches;
   G4H_CUDA(cudaGetLastError());
@@ -376,6 +394,7 @@ int LaunchElectronHowFar(G4HB200* h, G4HB200ElectronBatch* dev, uint64_t seed, v
   if ((rc = EnsureElectronWork(h->slots[0], dev->n)) != 0) return rc;
   const ElectronWork& w = h->slots[0].work;
   StageTimer t{h, static_cast<cudaStream_t>(stream)};
+  h->PinTables(t.st);
   G4H_CUDA(cudaMemsetAsync(w.count, 0, kNumElQueues * sizeof(int32_t), t.st));
   rc = LaunchHowFarStages<true>(h, dev, w, seed, t.st, t);
   if (rc != 0) return rc;
@@ -403,6 +422,7 @@ int LaunchElectronPipeline(G4HB200* h, G4HB200ElectronBatch* dev, G4HB200Seconda
   if (dev->n > 0x7fffffff) return Fail(G4HB200_EINVAL, "batch too large (track indices are 32 bit)");
   if ((rc = EnsureElectronWork(h->slots[slotIndex], dev->n)) != 0) return rc;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  h->PinTables(st);
   const int64_t n = dev->n;
   ElectronWork w = h->slots[slotIndex].work;
   if (slab != nullptr) w.steppre = h->slots[slotIndex].steppreMem;
@@ -415,6 +435,7 @@ int LaunchElectronPipeline(G4HB200* h, G4HB200ElectronBatch* dev, G4HB200Seconda
   G4H_CUDA(t.After(stage))
   G4HB200::WorkSlot& slot = h->slots[slotIndex];
   if ((rc = EnsureAuxStreams(slot)) != 0) return rc;
+  for (auto& a : slot.aux) h->PinTables(a);
   if (kFused && slab != nullptr) {
     G4H_STAGE(kSStepHead, ShowerElectronHeadKernel<<<OneWave(h, ShowerElectronHeadKernel, n), kThreadsPerBlock, 0, st>>>(
                               h->view, *dev, w, seed, slab->g, slab->geo));
@@ -500,6 +521,8 @@ int LaunchGammaPipeline(G4HB200* h, G4HB200GammaBatch* dev, G4HB200SecondaryQueu
   if ((rc = EnsureElectronWork(slot, dev->n)) != 0) return rc;
   if ((rc = EnsureAuxStreams(slot)) != 0) return rc;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  h->PinTables(st);
+  for (auto& a : slot.aux) h->PinTables(a);
   const int64_t n = dev->n;
   const ElectronWork& w = slot.work;
   G4H_CUDA(cudaMemsetAsync(w.count, 0, kNumElQueues * sizeof(int32_t), st));
@@ -888,6 +911,18 @@ int g4hb200_create(const G4HB200Tables* tables, int device, G4HB200** out) {
     }
   }
   h->view = MakeView(d);
+  {
+    const char* env = std::getenv("G4HB200_L2_PERSIST");
+    int maxPersist = 0;
+    if (!(env != nullptr && env[0] == '0') &&
+        cudaDeviceGetAttribute(&maxPersist, cudaDevAttrMaxPersistingL2CacheSize, device) == cudaSuccess && maxPersist > 0) {
+      const size_t want = h->arenaBytes < static_cast<size_t>(maxPersist) ? h->arenaBytes : static_cast<size_t>(maxPersist);
+      size_t have = 0;
+      cudaDeviceGetLimit(&have, cudaLimitPersistingL2CacheSize);
+      if (have >= want || cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want) == cudaSuccess) h->l2Persist = true;
+      cudaGetLastError();
+    }
+  }
   {
     if (const char* fu = std::getenv("G4HB200_FUSED")) h->fusedBelow = fu[0] != '0' ? (int64_t{1} << 62) : 0;
     if (const char* fb = std::getenv("G4HB200_FUSED_BELOW")) h->fusedBelow = std::atoll(fb);

@@ -161,6 +161,9 @@ struct G4HB200 {
   std::unordered_map<const void*, int> residentCtas;  // per kernel: CTAs of kThreadsPerBlock threads that fit on one SM
   // The table arena (< 1 MB) as a persisting L2 access-policy window on every stream the library launches on: track state
   // streams through L2 at hundreds of MB per step, the tables must not be evicted by it.  G4HB200_L2_PERSIST=0 turns it off.
+  // rejection samplers with lane refill (g4h_refill.cuh): 32-entry chunks a warp gets at least; 0: the one-thread-per-track
+  // samplers (G4HB200_REFILL)
+  int refillChunks = 0;
   bool l2Persist = false;
   std::unordered_set<cudaStream_t> pinnedStreams;
   void PinTables(cudaStream_t st) {
@@ -189,6 +192,23 @@ int OneWave(G4HB200* h, K kernel, int64_t n) {
   if (it == h->residentCtas.end()) {
     int perSM = 0;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, kernel, kThreadsPerBlock, 0) != cudaSuccess || perSM < 1) perSM = 1;
+    it = h->residentCtas.emplace(key, perSM).first;
+  }
+  return GridFor(n, h->smCount, it->second);
+}
+
+// the same for a kernel with dynamic shared memory (the refill samplers, g4h_refill.cuh)
+template <class K>
+int OneWaveSmem(G4HB200* h, K kernel, int64_t n, size_t smemBytes) {
+  const void* key = reinterpret_cast<const void*>(kernel);
+  auto it = h->residentCtas.find(key);
+  if (it == h->residentCtas.end()) {
+    int perSM = 0;
+    if (cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smemBytes)) != cudaSuccess ||
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, kernel, kThreadsPerBlock, smemBytes) != cudaSuccess || perSM < 1) {
+      cudaGetLastError();
+      perSM = 1;
+    }
     it = h->residentCtas.emplace(key, perSM).first;
   }
   return GridFor(n, h->smCount, it->second);
@@ -474,10 +494,20 @@ int LaunchElectronPipeline(G4HB200* h, G4HB200ElectronBatch* dev, G4HB200Seconda
   G4H_CUDA(t.Before(stage, on));    \
   __VA_ARGS__;                      \
   G4H_CUDA(t.After(stage, on))
-  G4H_STAGE(kSRB, st, ElSamplerKernel<kQRB><<<OneWave(h, ElSamplerKernel<kQRB>, n), kThreadsPerBlock, 0, st>>>(h->view, *dev, w, *sec, seed));
-  G4H_STAGE(kSSB, side[0], ElSamplerKernel<kQSB><<<OneWave(h, ElSamplerKernel<kQSB>, n), kThreadsPerBlock, 0, side[0]>>>(h->view, *dev, w, *sec, seed));
-  G4H_STAGE(kSBhabha, side[1], ElSamplerKernel<kQBhabha><<<OneWave(h, ElSamplerKernel<kQBhabha>, n), kThreadsPerBlock, 0, side[1]>>>(h->view, *dev, w, *sec, seed));
-  G4H_STAGE(kSMoller, side[2], ElSamplerKernel<kQMoller><<<OneWave(h, ElSamplerKernel<kQMoller>, n), kThreadsPerBlock, 0, side[2]>>>(h->view, *dev, w, *sec, seed));
+  const int rc4 = h->refillChunks;
+#define G4H_EL_SAMPLER(stage, on, Q)                                                                                                     \
+  if (rc4 > 0) {                                                                                                                         \
+    constexpr size_t smem = RefillSmemBytes<ElRefillSampler<Q>::type>();                                                                 \
+    G4H_STAGE(stage, on, ElRefillSamplerKernel<Q><<<OneWaveSmem(h, ElRefillSamplerKernel<Q>, n, smem), kThreadsPerBlock, smem, on>>>(   \
+                             h->view, *dev, w, *sec, seed, rc4));                                                                        \
+  } else {                                                                                                                               \
+    G4H_STAGE(stage, on, ElSamplerKernel<Q><<<OneWave(h, ElSamplerKernel<Q>, n), kThreadsPerBlock, 0, on>>>(h->view, *dev, w, *sec, seed)); \
+  }
+  G4H_EL_SAMPLER(kSRB, st, kQRB)
+  G4H_EL_SAMPLER(kSSB, side[0], kQSB)
+  G4H_EL_SAMPLER(kSBhabha, side[1], kQBhabha)
+  G4H_EL_SAMPLER(kSMoller, side[2], kQMoller)
+#undef G4H_EL_SAMPLER
   G4H_STAGE(kSAnnih, side[3], ElSamplerKernel<kQAnnih><<<OneWave(h, ElSamplerKernel<kQAnnih>, n), kThreadsPerBlock, 0, side[3]>>>(h->view, *dev, w, *sec, seed));
   G4H_STAGE(kSAtRest, side[4], ElSamplerKernel<kQAtRest><<<OneWave(h, ElSamplerKernel<kQAtRest>, n), kThreadsPerBlock, 0, side[4]>>>(h->view, *dev, w, *sec, seed));
   if (!alone) {
@@ -542,15 +572,20 @@ int LaunchGammaPipeline(G4HB200* h, G4HB200GammaBatch* dev, G4HB200SecondaryQueu
     G4H_CUDA(cudaEventRecord(slot.fork, st));
     for (int k = 0; k < 2; ++k) G4H_CUDA(cudaStreamWaitEvent(slot.aux[k], slot.fork, 0));
   }
-  G4H_CUDA(t.Before(kSGammaCompton, st));
-  GammaInteractKernel<kGQCompton><<<OneWave(h, GammaInteractKernel<kGQCompton>, n), kThreadsPerBlock, 0, st>>>(h->view, *dev, w, *sec, seed);
-  G4H_CUDA(t.After(kSGammaCompton, st));
-  G4H_CUDA(t.Before(kSGammaConversion, side[0]));
-  GammaInteractKernel<kGQConversion><<<OneWave(h, GammaInteractKernel<kGQConversion>, n), kThreadsPerBlock, 0, side[0]>>>(h->view, *dev, w, *sec, seed);
-  G4H_CUDA(t.After(kSGammaConversion, side[0]));
-  G4H_CUDA(t.Before(kSGammaPhotoelectric, side[1]));
-  GammaInteractKernel<kGQPhotoelectric><<<OneWave(h, GammaInteractKernel<kGQPhotoelectric>, n), kThreadsPerBlock, 0, side[1]>>>(h->view, *dev, w, *sec, seed);
-  G4H_CUDA(t.After(kSGammaPhotoelectric, side[1]));
+  const int rc4 = h->refillChunks;
+#define G4H_GM_SAMPLER(stage, on, P)                                                                                                  \
+  G4H_CUDA(t.Before(stage, on));                                                                                                      \
+  if (rc4 > 0) {                                                                                                                      \
+    constexpr size_t smem = RefillSmemBytes<GammaRefillSampler<P>::type>();                                                           \
+    GammaRefillKernel<P><<<OneWaveSmem(h, GammaRefillKernel<P>, n, smem), kThreadsPerBlock, smem, on>>>(h->view, *dev, w, *sec, seed, rc4); \
+  } else {                                                                                                                            \
+    GammaInteractKernel<P><<<OneWave(h, GammaInteractKernel<P>, n), kThreadsPerBlock, 0, on>>>(h->view, *dev, w, *sec, seed);          \
+  }                                                                                                                                   \
+  G4H_CUDA(t.After(stage, on));
+  G4H_GM_SAMPLER(kSGammaCompton, st, kGQCompton)
+  G4H_GM_SAMPLER(kSGammaConversion, side[0], kGQConversion)
+  G4H_GM_SAMPLER(kSGammaPhotoelectric, side[1], kGQPhotoelectric)
+#undef G4H_GM_SAMPLER
   if (!alone) {
     for (int k = 0; k < 2; ++k) {
       G4H_CUDA(cudaEventRecord(slot.join[k], slot.aux[k]));
@@ -923,6 +958,7 @@ int g4hb200_create(const G4HB200Tables* tables, int device, G4HB200** out) {
       cudaGetLastError();
     }
   }
+  if (const char* rf = std::getenv("G4HB200_REFILL")) h->refillChunks = std::atoi(rf) < 0 ? 0 : std::atoi(rf);
   {
     if (const char* fu = std::getenv("G4HB200_FUSED")) h->fusedBelow = fu[0] != '0' ? (int64_t{1} << 62) : 0;
     if (const char* fb = std::getenv("G4HB200_FUSED_BELOW")) h->fusedBelow = std::atoll(fb);

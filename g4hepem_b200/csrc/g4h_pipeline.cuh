@@ -23,6 +23,7 @@
 
 #include "g4h_kernels.cuh"
 #include "g4h_perform_stages.cuh"
+#include "g4h_refill.cuh"
 #include "g4h_stages.cuh"
 
 namespace g4h {
@@ -230,6 +231,43 @@ GammaInteractKernel(const __grid_constant__ TablesView tv, const __grid_constant
     }
     AppendSecondaries(cc, sq, sec, id, i);
   }
+}
+
+// ---- the rejection samplers with lane refill (g4h_refill.cuh): one warp = one stream of queue entries -----------------------
+template <int kQueue> struct ElRefillSampler;
+template <> struct ElRefillSampler<kQMoller> { using type = MollerSampler; };
+template <> struct ElRefillSampler<kQBhabha> { using type = BhabhaSampler; };
+template <> struct ElRefillSampler<kQSB>     { using type = SBSampler; };
+template <> struct ElRefillSampler<kQRB>     { using type = RBSampler; };
+template <int kProc> struct GammaRefillSampler;
+template <> struct GammaRefillSampler<kGQConversion>    { using type = ConversionSampler; };
+template <> struct GammaRefillSampler<kGQCompton>       { using type = ComptonSampler; };
+template <> struct GammaRefillSampler<kGQPhotoelectric> { using type = PhotoelectricSampler; };
+
+// dynamic shared memory of a refill kernel: one RefillWarpStore per warp
+template <class S>
+constexpr size_t RefillSmemBytes() { return sizeof(RefillWarpStore<S>) * kWarpsPerBlock; }
+
+template <int kQueue>
+__global__ void __launch_bounds__(kThreadsPerBlock, G4H_MINB_QUEUE)
+ElRefillSamplerKernel(const __grid_constant__ TablesView tv, const __grid_constant__ G4HB200ElectronBatch b,
+                      const __grid_constant__ ElectronWork w, const __grid_constant__ G4HB200SecondaryQueue sq, uint64_t seed,
+                      int chunksPerWarp) {
+  using S = typename ElRefillSampler<kQueue>::type;
+  extern __shared__ __align__(16) unsigned char refillSmem[];
+  RefillWarpStore<S>* store = reinterpret_cast<RefillWarpStore<S>*>(refillSmem);
+  RefillSamplerWarp<S, ElectronSamplerIO>(tv, b, w.queue[kQueue], w.count[kQueue], sq, seed, chunksPerWarp, store[threadIdx.x >> 5]);
+}
+
+template <int kProc>
+__global__ void __launch_bounds__(kThreadsPerBlock, G4H_MINB_QUEUE)
+GammaRefillKernel(const __grid_constant__ TablesView tv, const __grid_constant__ G4HB200GammaBatch b,
+                  const __grid_constant__ ElectronWork w, const __grid_constant__ G4HB200SecondaryQueue sq, uint64_t seed,
+                  int chunksPerWarp) {
+  using S = typename GammaRefillSampler<kProc>::type;
+  extern __shared__ __align__(16) unsigned char refillSmem[];
+  RefillWarpStore<S>* store = reinterpret_cast<RefillWarpStore<S>*>(refillSmem);
+  RefillSamplerWarp<S, GammaSamplerIO>(tv, b, w.queue[kProc], w.count[kProc], sq, seed, chunksPerWarp, store[threadIdx.x >> 5]);
 }
 
 }  // namespace g4h

@@ -530,7 +530,7 @@ G4H_FN void StageGammaInteract(const TablesView& tv, const G4HB200GammaBatch& b,
   rng.Init(seed, static_cast<uint32_t>(m.id), static_cast<uint32_t>(m.draw), false, 0.0);
   if (windowSlots != 0u) rng.FillWindow(window, windowStride, windowSlots);
   if (kProc == 0) PerformConversion(tv, s, rng, sec);
-  if (kProc == 1) PerformCompton(s, rng, sec);
+  if (kProc == 1) PerformCompton(tv, s, rng, sec);
   if (kProc == 2) PerformPhotoelectric(tv, s, rng, sec);
   const double finalEkin = s.ekin;
   if (finalEkin > 0.0 && finalEkin <= tv.gammaTrackingCut) {

@@ -138,7 +138,7 @@ GammaTrackOpKernel(const __grid_constant__ TablesView tv, const __grid_constant_
           const int iDProc = s.winner;
           if (iDProc == 0) s.nIA0 = -1.0;  // SetNumIALeft(-1, iDProc): only slot 0 is live state of a gamma
           if (iDProc == 0) PerformConversion(tv, s, rng, sec);
-          if (iDProc == 1) PerformCompton(s, rng, sec);
+          if (iDProc == 1) PerformCompton(tv, s, rng, sec);
           if (iDProc == 2) PerformPhotoelectric(tv, s, rng, sec);
           const double finalEkin = s.ekin;
           if (finalEkin > 0.0 && finalEkin <= tv.gammaTrackingCut) {

@@ -475,3 +475,45 @@ def test_fused_launch_and_stage_pipeline_agree(engine, flat_tables):
             assert len(ra["ekin"]) == len(rb["ekin"])
             for k in ("parent_index", "slot", "ekin", "kind", "parent_id", "dir"):
                 assert np.array_equal(ra[k], rb[k]), (n, k)
+
+
+def test_refill_samplers_and_per_track_samplers_agree(engine, flat_tables):
+    """The rejection samplers a warp at a time with lane refill (g4h_refill.cuh, G4HB200_REFILL=k) and one thread per
+    track (the default) run the same Setup / Trial / Finish pieces (g4h_samplers.cuh) on the same per-track uniform
+    streams, only in another order and with the uniforms of a pass generated inside the pass: state, results and
+    secondaries must agree bit for bit, for a supply of 1 and of 4 chunks per warp and for a ragged batch."""
+    import os
+
+    import torch
+
+    from g4hepem_b200 import engine as eng
+
+    refill = []
+    for k in ("1", "4"):
+        os.environ["G4HB200_REFILL"] = k
+        try:
+            refill.append(eng.Engine(flat_tables, device=0))
+        finally:
+            del os.environ["G4HB200_REFILL"]
+    for n in (300007, 1000):
+        host = batches.make_electron_batch(n, flat_tables.num_matcut, seed=191)
+        ghost = batches.make_gamma_batch(n, flat_tables.num_matcut, boundary_fraction=0.1, seed=192)
+        outs = []
+        for e in [engine] + refill:
+            dev, sec = eng.ElectronDeviceBatch(n), eng.SecondaryDeviceQueue(2 * n)
+            dev.upload(host)
+            eng.ElectronManager.Step(e, dev, sec, SEED)
+            torch.cuda.synchronize()
+            step = (dev.download(), sec.download().sorted_records())
+            gdev, gsec = eng.GammaDeviceBatch(n), eng.SecondaryDeviceQueue(2 * n)
+            gdev.upload(ghost)
+            eng.GammaManager.Step(e, gdev, gsec, SEED)
+            torch.cuda.synchronize()
+            outs.append((step, (gdev.download(), gsec.download().sorted_records())))
+        for other in outs[1:]:
+            for (a, ra), (b, rb) in zip(outs[0], other):
+                for g in a.groups()[:10] + ("meta", "winner"):
+                    assert np.array_equal(getattr(a, g), getattr(b, g), equal_nan=True), (n, g)
+                assert len(ra["ekin"]) == len(rb["ekin"])
+                for k in ("parent_index", "slot", "ekin", "kind", "parent_id", "dir"):
+                    assert np.array_equal(ra[k], rb[k]), (n, k)

@@ -399,6 +399,37 @@ def run_gpu(args):
                              "between the per-step CUDA events; value = tracks / summed step time"}
         del pristine_dev
 
+    # ---- offered variant: SampleMSC in single precision (g4hb200_set_msc_precision(h, 32), tests/test_msc_f32.py states the
+    # bound); the same timed region as `value`, a record beside it -- the headline is the FP64 drop-in -----------------------------
+    variants = None
+    if args.variants:
+        in_groups_dev = batches.ElectronHostBatch.PAIR_GROUPS + ("meta",)
+        for i in range(ring_n):
+            ring[i].upload(pristine, groups=in_groups_dev)
+        engine.set_msc_precision(32)
+        try:
+            for i in range(warmup):
+                sec.reset()
+                eng.ElectronManager.Step(engine, ring[i % ring_n], sec, SEED)
+            barrier()
+            v0, v1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            v0.record()
+            for i in range(steps):
+                sec.reset()
+                eng.ElectronManager.Step(engine, ring[(warmup + i) % ring_n], sec, SEED)
+            v1.record()
+            barrier()
+        finally:
+            engine.set_msc_precision(64)
+        v_ms = v0.elapsed_time(v1)
+        if dist is not None:
+            t = torch.tensor([v_ms], dtype=torch.float64, device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            v_ms = float(t.item())
+        variants = {"msc_f32": {"value": world * n * steps / (v_ms * 1e-3), "unit": UNIT, "ms_per_step": v_ms / steps, "dtype": "f64 + f32 SampleMSC",
+                                "bound": "discrete outcomes, energies, step lengths identical to the f64 path; direction within 5e-4 "
+                                         "absolute (99.9 %: 1e-5), displacement within 2e-4 of its length (tests/test_msc_f32.py)"}}
+
     # ---- BASELINE configs[4]: TestEm3 ATLASbar 10 GeV e- showers, primaries sharded over the ranks, the per-layer deposits
     # summed over ranks by ONE NCCL all_reduce on the device -- inside the timed region ---------------------------------------
     shower_rec = None
@@ -516,6 +547,8 @@ def run_gpu(args):
         line["sustained"] = sustained
     if shower_rec is not None:
         line["shower"] = shower_rec
+    if variants is not None:
+        line["variants"] = variants
     if not args.no_cpu_baseline and world == 1:
         try:
             v, threads, kind, times = _cpu_reference_rate(min(n, args.cpu_sample), 3)
@@ -569,6 +602,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-affinity", action="store_true", help="leave the CPU affinity of the ranks alone")
     ap.add_argument("--sustained-seconds", type=float, default=1.0, help="length of the sustained-load loop (0: skip)")
+    ap.add_argument("--no-variants", dest="variants", action="store_false", help="skip the offered-variant records (f32 SampleMSC)")
     ap.add_argument("--shower-primaries", type=int, default=4096, help="BASELINE configs[4] record: primaries per GPU (0: skip)")
     args = ap.parse_args()
     if args.impl == "reference":

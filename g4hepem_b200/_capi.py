@@ -238,6 +238,7 @@ PROTOTYPES = {
     "g4hb200_gamma_step_host": (C.c_int, [_H, C.POINTER(GammaBatch), C.POINTER(SecondaryQueue), C.c_uint64]),
     "g4hb200_launch_count": (C.c_int64, [_H]),
     "g4hb200_set_kernel_timing": (C.c_int, [_H, C.c_int]),
+    "g4hb200_set_msc_precision": (C.c_int, [_H, C.c_int]),
     "g4hb200_kernel_times": (C.c_int, [_H, _vp, _vp, _vp]),
     "g4hb200_stage_name": (C.c_char_p, [C.c_int]),
     "g4hb200_shower_run": (C.c_int, [_H, C.POINTER(SlabGeometry), C.c_int64, C.c_int32, C.c_double, C.c_uint64, C.c_int32,

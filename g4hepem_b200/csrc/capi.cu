@@ -164,6 +164,8 @@ struct G4HB200 {
   // rejection samplers with lane refill (g4h_refill.cuh): 32-entry chunks a warp gets at least; 0: the one-thread-per-track
   // samplers (G4HB200_REFILL)
   int refillChunks = 0;
+  // SampleMSC in single precision (g4h_msc_f32.cuh), an offered variant: g4hb200_set_msc_precision(h, 32)
+  bool mscF32 = false;
   bool l2Persist = false;
   std::unordered_set<cudaStream_t> pinnedStreams;
   void PinTables(cudaStream_t st) {
@@ -474,10 +476,17 @@ int LaunchElectronPipeline(G4HB200* h, G4HB200ElectronBatch* dev, G4HB200Seconda
     G4H_CUDA(cudaEventRecord(slot.fork, st));
     G4H_CUDA(cudaStreamWaitEvent(slot.aux[0], slot.fork, 0));
   }
-  G4H_STAGE(kSMscEl, ElMSCSampleKernel<false><<<OneWave(h, ElMSCSampleKernel<false>, n), kThreadsPerBlock, 0, st>>>(h->view, *dev, w, seed));
-  G4H_CUDA(t.Before(kSMscPos, side[0]));
-  ElMSCSampleKernel<true><<<OneWave(h, ElMSCSampleKernel<true>, n), kThreadsPerBlock, 0, side[0]>>>(h->view, *dev, w, seed);
-  G4H_CUDA(t.After(kSMscPos, side[0]));
+  if (h->mscF32) {
+    G4H_STAGE(kSMscEl, ElMSCSampleF32Kernel<false><<<OneWave(h, ElMSCSampleF32Kernel<false>, n), kThreadsPerBlock, 0, st>>>(h->view, *dev, w, seed));
+    G4H_CUDA(t.Before(kSMscPos, side[0]));
+    ElMSCSampleF32Kernel<true><<<OneWave(h, ElMSCSampleF32Kernel<true>, n), kThreadsPerBlock, 0, side[0]>>>(h->view, *dev, w, seed);
+    G4H_CUDA(t.After(kSMscPos, side[0]));
+  } else {
+    G4H_STAGE(kSMscEl, ElMSCSampleKernel<false><<<OneWave(h, ElMSCSampleKernel<false>, n), kThreadsPerBlock, 0, st>>>(h->view, *dev, w, seed));
+    G4H_CUDA(t.Before(kSMscPos, side[0]));
+    ElMSCSampleKernel<true><<<OneWave(h, ElMSCSampleKernel<true>, n), kThreadsPerBlock, 0, side[0]>>>(h->view, *dev, w, seed);
+    G4H_CUDA(t.After(kSMscPos, side[0]));
+  }
   if (!alone) {
     G4H_CUDA(cudaEventRecord(slot.join[0], slot.aux[0]));
     G4H_CUDA(cudaStreamWaitEvent(st, slot.join[0], 0));
@@ -958,6 +967,7 @@ int g4hb200_create(const G4HB200Tables* tables, int device, G4HB200** out) {
       cudaGetLastError();
     }
   }
+  if (const char* mf = std::getenv("G4HB200_MSC_F32")) h->mscF32 = mf[0] == '1';
   if (const char* rf = std::getenv("G4HB200_REFILL")) h->refillChunks = std::atoi(rf) < 0 ? 0 : std::atoi(rf);
   {
     if (const char* fu = std::getenv("G4HB200_FUSED")) h->fusedBelow = fu[0] != '0' ? (int64_t{1} << 62) : 0;
@@ -1549,6 +1559,14 @@ int g4hb200_set_kernel_timing(G4HB200* h, int enable) {
   int rc = CheckHandle(h);
   if (rc != 0) return rc;
   h->timing = enable != 0;
+  return 0;
+}
+
+int g4hb200_set_msc_precision(G4HB200* h, int bits) {
+  int rc = CheckHandle(h);
+  if (rc != 0) return rc;
+  if (bits != 32 && bits != 64) return Fail(G4HB200_EINVAL, "MSC precision must be 32 or 64");
+  h->mscF32 = bits == 32;
   return 0;
 }
 

@@ -22,6 +22,7 @@
 #define G4H_PIPELINE_CUH
 
 #include "g4h_kernels.cuh"
+#include "g4h_msc_f32.cuh"
 #include "g4h_perform_stages.cuh"
 #include "g4h_refill.cuh"
 #include "g4h_stages.cuh"
@@ -118,6 +119,28 @@ ElMSCSampleKernel(const __grid_constant__ TablesView tv, const __grid_constant__
       route = StageMSCSample<kPositron>(tv, b, w.prestep, i, seed, cbeta1, w.steppre);
     }
     // kQFluct, kQDiscrete, kQAtRest are three consecutive queues
+    RouteToQueues<3>(cc, route < 0 ? -1 : route - kQFluct, i, w.queue + kQFluct, w.count + kQFluct);
+  }
+}
+
+// the offered single-precision variant (g4h_msc_f32.cuh; g4hb200_set_msc_precision(h, 32))
+template <bool kPositron>
+__global__ void __launch_bounds__(kThreadsPerBlock, 4)
+ElMSCSampleF32Kernel(const __grid_constant__ TablesView tv, const __grid_constant__ G4HB200ElectronBatch b,
+                     const __grid_constant__ ElectronWork w, uint64_t seed) {
+  const int cnt = w.count[kPositron ? kQMscPos : kQMscEl];
+  const int32_t* queue = w.queue[kPositron ? kQMscPos : kQMscEl];
+  const int nRound = static_cast<int>(RoundUpToCta(cnt));
+  const int stride = gridDim.x * blockDim.x;
+  __shared__ CtaCounters<3> cc;
+  cc.Init();
+  for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < nRound; q += stride) {
+    int route = -1;
+    int32_t i = 0;
+    if (q < cnt) {
+      i = queue[q];
+      route = StageMSCSampleF32<kPositron>(tv, b, w.prestep, i, seed, w.steppre);
+    }
     RouteToQueues<3>(cc, route < 0 ? -1 : route - kQFluct, i, w.queue + kQFluct, w.count + kQFluct);
   }
 }

@@ -60,6 +60,10 @@ class Engine:
     def launch_count(self):
         return int(self.lib.g4hb200_launch_count(self.handle))
 
+    def set_msc_precision(self, bits):
+        """64: the drop-in path (default); 32: the offered single-precision SampleMSC (csrc/g4h_msc_f32.cuh)."""
+        _capi.check(self.lib.g4hb200_set_msc_precision(self.handle, int(bits)), "set_msc_precision")
+
     def set_kernel_timing(self, enable=True):
         _capi.check(self.lib.g4hb200_set_kernel_timing(self.handle, int(enable)), "set_kernel_timing")
 

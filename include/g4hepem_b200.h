@@ -341,6 +341,17 @@ int g4hb200_set_kernel_timing(G4HB200* h, int enable);
 int g4hb200_kernel_times(G4HB200* h, double* ms_sum, int64_t* launches, int64_t* items);
 const char* g4hb200_stage_name(int k);
 
+/* ---- offered variant: multiple scattering in single precision ----------------------------------------------------
+ * SURVEY.md 8(f) rank 4; the reference's authors: "all these could probably be computed in float"
+ * (G4HepEm/G4HepEmRun/include/G4HepEmElectronInteractionUMSC.icc:296,312).  bits = 32: G4HepEmElectronManager::SampleMSC
+ * (G4HepEmElectronManager.icc:261-322, UMSC.icc:129-357) inside g4hb200_electron_step / _perform and the stepping loops
+ * computes the Urban model parameters and samples the polar angle in float (csrc/g4h_msc_f32.cuh); bits = 64 (the
+ * default): the drop-in, bit-exact path.  With 32 everything but the post-step direction and the MSC displacement is
+ * still identical to the reference for all but a few tracks in a million (those whose model regime is decided within
+ * float rounding of a threshold consume a different number of uniforms); direction and displacement agree with the FP64
+ * path within the bound stated and tested in tests/test_msc_f32.py.  Returns G4HB200_EINVAL for any other value. */
+int g4hb200_set_msc_precision(G4HB200* h, int bits);
+
 /* ---- stepping loop over a slab calorimeter (BASELINE configs[4]) -----------------------------------------------
  * The loop the reference's callers run around the managers -- G4HepEmTrackingManager::TrackElectron / TrackGamma
  * (G4HepEm/G4HepEm/src/G4HepEmTrackingManager.cc:428-705,985-1140) inside the TestEm3 sampling calorimeter

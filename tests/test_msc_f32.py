@@ -1,0 +1,75 @@
+"""The offered single-precision SampleMSC (g4hb200_set_msc_precision(h, 32), csrc/g4h_msc_f32.cuh)
+against the FP64 drop-in path on the same batch and the same uniform streams.
+
+Stated bound (north-star: "within a stated bound if an FP32 variant is offered"), measured on 1M tracks of BASELINE
+configs[2] (tools/msc_f32_probe.py, profiles/r02b_msc_f32_probe.json) and asserted here with a margin:
+  * discrete outcome (flags incl. fIsNoScatteringInMSC, uniforms consumed, winner, secondary counts): identical for
+    at least 99.99 % of the tracks (measured: all of them); for those, energies, step lengths, interaction lengths and
+    the secondaries' energies are bit-identical to the FP64 path -- the variant only touches direction and displacement;
+  * post-step direction: every component within 5e-4 absolute (measured 7.9e-5), 99.9 % within 1e-5 (measured 1.7e-6), unit
+    length to 1e-14;
+  * polar deflection angle above 1 mrad: within 2 % relative (measured 0.4 %), 99.9 % within 2e-4 (measured 3.7e-5);
+  * MSC displacement: within 2e-4 of its length (measured 3.2e-5).
+"""
+import numpy as np
+import pytest
+
+from g4hepem_b200 import batches
+
+pytestmark = pytest.mark.gpu
+SEED = 2026
+
+
+def _dirs(b):
+    return np.concatenate([b.dirx_diry, b.dirz_safety[:, :1]], axis=1)
+
+
+def test_msc_f32_variant_within_stated_bound(engine, flat_tables):
+    import torch
+
+    from g4hepem_b200 import engine as eng
+
+    n = 1 << 20
+    host = batches.make_electron_batch(n, flat_tables.num_matcut, seed=31)
+    dev, sec = eng.ElectronDeviceBatch(n), eng.SecondaryDeviceQueue(2 * n)
+    out = {}
+    try:
+        for bits in (64, 32):
+            engine.set_msc_precision(bits)
+            dev.upload(host)
+            sec.reset()
+            eng.ElectronManager.Step(engine, dev, sec, SEED)
+            torch.cuda.synchronize()
+            out[bits] = (dev.download(), sec.download().sorted_records())
+    finally:
+        engine.set_msc_precision(64)
+    with pytest.raises(Exception):
+        engine.set_msc_precision(16)
+    (a, ra), (b, rb) = out[64], out[32]
+    same = (a.meta == b.meta).all(axis=1) & (a.winner == b.winner)
+    assert same.mean() >= 0.9999
+    for g in ("ekin_logekin", "gstep_pstep", "nia01", "nia23", "msc_irange_dynrf", "msc_tlimmin_gauss"):
+        assert np.array_equal(getattr(a, g)[same], getattr(b, g)[same], equal_nan=True), g
+    assert np.array_equal(a.edep_dispx[same, 0], b.edep_dispx[same, 0])
+    if same.all():
+        assert len(ra["ekin"]) == len(rb["ekin"])
+        for k in ("parent_index", "slot", "ekin", "kind", "parent_id"):
+            assert np.array_equal(ra[k], rb[k]), k
+    for g in ("dirx_diry", "dirz_safety", "edep_dispx", "dispy_dispz"):
+        assert not np.isnan(getattr(b, g)).any(), g
+    d64, d32, d0 = _dirs(a), _dirs(b), _dirs(host)
+    dd = np.abs(d64 - d32).max(axis=1)[same]
+    assert dd.max() <= 5e-4
+    assert np.quantile(dd, 0.999) <= 1e-5
+    assert np.abs((d32 ** 2).sum(axis=1) - 1.0).max() <= 1e-14
+    ang64 = np.sqrt(np.maximum(2.0 * (1.0 - np.clip((d64 * d0).sum(axis=1), -1, 1)), 0))
+    ang32 = np.sqrt(np.maximum(2.0 * (1.0 - np.clip((d32 * d0).sum(axis=1), -1, 1)), 0))
+    big = same & (ang64 > 1e-3)
+    rel = np.abs(ang32[big] - ang64[big]) / ang64[big]
+    assert rel.max() <= 2e-2
+    assert np.quantile(rel, 0.999) <= 2e-4
+    p64 = np.concatenate([a.edep_dispx[:, 1:], a.dispy_dispz], axis=1)
+    p32 = np.concatenate([b.edep_dispx[:, 1:], b.dispy_dispz], axis=1)
+    length = np.linalg.norm(p64, axis=1)
+    has = same & (length > 0)
+    assert (np.linalg.norm(p64 - p32, axis=1)[has] / length[has]).max() <= 2e-4

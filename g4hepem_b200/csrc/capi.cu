@@ -1462,6 +1462,8 @@ int g4hb200_electron_step_host(G4HB200* h, G4HB200ElectronBatch* host, G4HB200Se
     if (v >= 1024) chunk = v;
   }
   while ((n + chunk - 1) / chunk > G4HB200::kMaxChunks) chunk *= 2;
+  // (equal chunks: a ramp of small first chunks, meant to start the device -> host direction earlier, measured 3 % slower --
+  // more chunks are more operations to enqueue, and the host's enqueue rate is what limits this call, profiles/r02b_ab2.log)
   const int numChunks = static_cast<int>((n + chunk - 1) / chunk);
   G4H_CUDA(cudaMemsetAsync(h->chunkCounters, 0, numChunks * sizeof(int32_t), h->slots[0].stream));
   G4H_CUDA(cudaStreamSynchronize(h->slots[0].stream));

@@ -574,7 +574,7 @@ NCU_NAMES = {"ElMSCSampleKernel<e->": "ElMSCSampleKernel<0>", "ElMSCSampleKernel
 def _traffic_from_profile(kernels):
     """dram bytes read + written by one 1M-track step = the sum over its kernels in the committed `ncu --set full` summary
     (unsplit 1M-track launches).  Returns (bytes or None, file)."""
-    for name in ("r02_pipeline_full.json", "r01c_pipeline_full.json"):
+    for name in ("r02b_pipeline_full.json", "r02_pipeline_full.json", "r01c_pipeline_full.json"):
         path = os.path.join(ROOT, "profiles", name)
         if not os.path.exists(path):
             continue

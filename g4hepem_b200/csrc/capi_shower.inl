@@ -103,7 +103,8 @@ int EnqueueTailIteration(G4HB200* h, const SlabGeom& g, ShowerStore& s, uint64_t
   // sizes the grids (a full wave: the populations may still grow); the kernels read the live counts from ShowerCtrl
   const int64_t nMax = s.score.capacity;
   int rc = 0;
-  ShowerIterKernel<<<1, 32, 0, st>>>(s.ctrl, s.score.nextCount, s.secEl.count, s.secGm.count, s.score.overflow);
+  ShowerIterKernel<<<1, 32, 0, st>>>(s.ctrl, s.score.nextCount, s.secEl.count, s.secGm.count, s.score.overflow, h->slots[0].work.count,
+                                     h->gmSlot.work.count);
   ++h->launches;
   G4H_CUDA(cudaEventRecord(h->loopFork, st));
   G4H_CUDA(cudaStreamWaitEvent(sg, h->loopFork, 0));

@@ -868,8 +868,15 @@ ShowerSecondaryKernel(const __grid_constant__ TablesView tv, const __grid_consta
 
 // ---- the top of an iteration of the graph-driven tail: what the host does between two iterations otherwise --------------------
 // (populations of the iteration <- what the previous one left in the next-step stores; counters back to zero; statistics)
+// elQueueCount / gmQueueCount: the interaction-queue counters of the two pipelines (they zero them again with a memset
+// node of their own; written here too so that every byte a kernel of the graph reads has been written by a kernel --
+// compute-sanitizer's initcheck does not follow memset nodes)
 __global__ void ShowerIterKernel(ShowerCtrl* ctrl, int32_t* nextCount, int32_t* secElCount, int32_t* secGmCount,
-                                 const int32_t* overflow) {
+                                 const int32_t* overflow, int32_t* elQueueCount, int32_t* gmQueueCount) {
+  if (blockIdx.x == 0 && threadIdx.x < kNumElQueues) {
+    elQueueCount[threadIdx.x] = 0;
+    gmQueueCount[threadIdx.x] = 0;
+  }
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
   ctrl->sumSec += static_cast<long long>(*secElCount) + *secGmCount;  // secondaries the previous iteration created
   // a store that ran out of capacity ends the run (the host reports it at its next look): nothing more is stepped

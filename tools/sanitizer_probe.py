@@ -24,4 +24,14 @@ r64 = e.electron_lookups(imc, ek, torch.log(ek), True)
 r32 = e.electron_lookups_f32(imc, ek.float(), torch.log(ek).float(), False)
 torch.cuda.synchronize()
 print("lookups", float(r64[0].sum()), float(r32[0].double().sum()))
+# the offered / opt-in paths: single-precision SampleMSC, lane-refill samplers (second engine: the switch is read at creation)
+e.set_msc_precision(32)
+dev.upload(host); sec.reset(); eng.ElectronManager.Step(e, dev, sec, 2026); torch.cuda.synchronize()
+e.set_msc_precision(64)
+os.environ["G4HB200_REFILL"] = "2"
+e2 = eng.Engine(ft, 0)
+del os.environ["G4HB200_REFILL"]
+dev.upload(host); sec.reset(); eng.ElectronManager.Step(e2, dev, sec, 2026); torch.cuda.synchronize()
+gd.upload(g); gs.reset(); eng.GammaManager.Step(e2, gd, gs, 2026); torch.cuda.synchronize()
+print("variants", int(sec.count[0].item()), int(gs.count[0].item()))
 print("done")

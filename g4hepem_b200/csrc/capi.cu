@@ -780,127 +780,6 @@ int LaunchElectronPipelineHalves(G4HB200* h, G4HB200ElectronBatch* dev, G4HB200S
     G4HB200ElectronBatch part = ElectronBatchView(*dev, lo, len);
     G4HB200SecondaryQueue q = *sec;
     q.parent_base = sec->parent_base + static_cast<int32_t>(lo);
-    double* prestep = h->slots[slotIndex].work.prestep + 2 * lo;
-    double* steppre = h->slots[slotIndex].steppreMem + 2 * lo;
-    if (slab != nullptr) {
-      TrackGeo geo = slab->geo;
-      geo.posx_posy += 2 * lo;
-      geo.posz_pad += 2 * lo;
-      geo.vol += lo;
-      geo.nextVol += lo;
-      geo.sub_left_eloss += 2 * lo;
-      geo.sub_pre += 2 * lo;
-      geo.sub_range_proc += 2 * lo;
-      ShowerElectronFusedKernel<<<FusedGrid(h, ShowerElectronFusedKernel, len), kThreadsPerBlock, 0, st>>>(h->view, part, prestep, steppre, q,
-                                                                                                       seed, slab->g, geo);
-    } else {
-      ElFusedStepKernel<kPerformOnly><<<FusedGrid(h, ElFusedStepKernel<kPerformOnly>, len), kThreadsPerBlock, 0, st>>>(h->view, part, prestep,
-                                                                                                                 q, seed);
-    }
-    ++h->launches;
-  }
-  --h->launches;  // After() counts one
-  G4H_CUDA(t.After(kSElFused));
-  if (t.tc != nullptr) G4H_CUDA(cudaEventRecord(t.tc->done, st));
-  G4H_CUDA(cudaGetLastError());
-  return 0;
-}
-
-template <int kMode>
-int LaunchGammaFused(G4HB200* h, G4HB200GammaBatch* dev, G4HB200SecondaryQueue* sec, uint64_t seed, void* stream,
-                     const SlabHead* slab = nullptr) {
-  int rc = CheckHandle(h);
-  if (rc != 0) return rc;
-  if (dev == nullptr || dev->n < 0) return Fail(G4HB200_EINVAL, "bad gamma batch");
-  if (sec == nullptr) return Fail(G4HB200_EINVAL, "secondary queue required");
-  if (dev->n == 0) return 0;
-  if (dev->n > 0x7fffffff) return Fail(G4HB200_EINVAL, "batch too large (track indices are 32 bit)");
-  cudaStream_t st = static_cast<cudaStream_t>(stream);
-  StageTimer t{h, st};
-  G4H_CUDA(t.Begin(dev->n));
-  const int fullGrid = FusedGrid(h, GammaFusedStepKernel<kMode>, dev->n);
-  const int64_t perLaunch = static_cast<int64_t>(fullGrid) * kFusedMaxTilesPerCta * kThreadsPerBlock;
-  G4H_CUDA(t.Before(kSGammaFused));
-  for (int64_t lo = 0; lo < dev->n; lo += perLaunch) {
-    const int64_t len = dev->n - lo < perLaunch ? dev->n - lo : perLaunch;
-    G4HB200GammaBatch part = GammaBatchView(*dev, lo, len);
-    G4HB200SecondaryQueue q = *sec;
-    q.parent_base = sec->parent_base + static_cast<int32_t>(lo);
-    if (kMode == 2 && slab != nullptr) {
-      TrackGeo geo = slab->geo;
-      geo.posx_posy += 2 * lo;
-      geo.posz_pad += 2 * lo;
-      geo.vol += lo;
-      geo.nextVol += lo;
-      ShowerGammaFusedKernel<<<FusedGrid(h, ShowerGammaFusedKernel, len), kThreadsPerBlock, 0, st>>>(h->view, part, q, seed, slab->g, geo);
-    } else {
-      GammaFusedStepKernel<kMode><<<FusedGrid(h, GammaFusedStepKernel<kMode>, len), kThreadsPerBlock, 0, st>>>(h->view, part, q, seed);
-    }
-    ++h->launches;
-  }
-  --h->launches;
-  G4H_CUDA(t.After(kSGammaFused));
-  if (t.tc != nullptr) G4H_CUDA(cudaEventRecord(t.tc->done, st));
-  G4H_CUDA(cudaGetLastError());
-  return 0;
-}
-
-// A sub-range of a batch (same struct, pointers advanced).
-G4HB200ElectronBatch ElectronBatchView(const G4HB200ElectronBatch& full, int64_t lo, int64_t len) {
-  G4HB200ElectronBatch v = full;
-  double** g[kNumElGroups];
-  ElectronDoubleGroups(&v, g);
-  for (int k = 0; k < kNumElGroups; ++k) if (*g[k] != nullptr) *g[k] += 2 * lo;
-  if (v.meta != nullptr) v.meta += 4 * lo;
-  if (v.winner != nullptr) v.winner += lo;
-  v.n = len;
-  return v;
-}
-
-// The pipeline of a large device batch as a few part-batch pipelines side by side (the caller's stream and internal
-// streams, fork / join by events).  The queue kernels at the end of a pipeline (discrete head, final state
-// samplers: 20-35 % of the issue slots, bound by gather latency and rejection loops) leave most of the machine idle;
-// with two halves in flight they run next to the other half's arithmetic-bound head / MSC / fluctuation kernels.
-// Tracks are independent and the uniform stream is keyed per track, so the result does not depend on the split.
-template <bool kFused>
-int LaunchElectronPipelineHalves(G4HB200* h, G4HB200ElectronBatch* dev, G4HB200SecondaryQueue* sec, uint64_t seed, void* stream,
-                                 const SlabHead* slab = nullptr) {
-  int rc = CheckHandle(h);
-  if (rc != 0) return rc;
-  if (dev == nullptr || sec == nullptr || dev->n < h->splitThreshold || h->timing || h->splitParts < 2) {
-    return LaunchElectronPipeline<kFused>(h, dev, sec, seed, stream, 0, slab);
-  }
-  if (dev->n > 0x7fffffff) return Fail(G4HB200_EINVAL, "batch too large (track indices are 32 bit)");
-  const int parts = h->splitParts;
-  for (int p = 1; p < parts; ++p) {
-    G4HB200::WorkSlot& other = h->slots[p];
-    if (other.stream == nullptr) {
-      G4H_CUDA(cudaStreamCreateWithFlags(&other.stream, cudaStreamNonBlocking));
-      G4H_CUDA(cudaEventCreateWithFlags(&other.counted, cudaEventDisableTiming));
-    }
-  }
-  if (h->splitFork == nullptr) {
-    G4H_CUDA(cudaEventCreateWithFlags(&h->splitFork, cudaEventDisableTiming));
-    for (auto& e : h->splitJoin) G4H_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-  }
-  cudaStream_t st = static_cast<cudaStream_t>(stream);
-  int64_t per = ((dev->n / parts + kThreadsPerBlock - 1) / kThreadsPerBlock) * kThreadsPerBlock;
-  // two parts: the first one gets splitFirst of the batch (its late stages then start while the larger second head runs)
-  int64_t first = per;
-  if (parts == 2) {
-    first = (static_cast<int64_t>(h->splitFirst * static_cast<double>(dev->n)) / kThreadsPerBlock) * kThreadsPerBlock;
-    if (first < kThreadsPerBlock) first = kThreadsPerBlock;
-    per = dev->n - first;
-  }
-  G4H_CUDA(cudaEventRecord(h->splitFork, st));
-  for (int p = 1; p < parts; ++p) G4H_CUDA(cudaStreamWaitEvent(h->slots[p].stream, h->splitFork, 0));
-  for (int p = 0; p < parts; ++p) {
-    const int64_t lo = p == 0 ? 0 : first + (p - 1) * per;
-    if (lo >= dev->n) break;
-    const int64_t len = p == 0 ? (first < dev->n ? first : dev->n) : ((p == parts - 1 || lo + per > dev->n) ? dev->n - lo : per);
-    G4HB200ElectronBatch part = ElectronBatchView(*dev, lo, len);
-    G4HB200SecondaryQueue q = *sec;
-    q.parent_base = sec->parent_base + static_cast<int32_t>(lo);
     cudaStream_t ps = p == 0 ? st : h->slots[p].stream;
     SlabHead partSlab;
     if (slab != nullptr) {

@@ -1,7 +1,7 @@
 #!/bin/bash
 # 8-GPU call with retries (the pod rarely has 8 free slots)
 for k in 1 2 3 4 5 6; do
-  /usr/local/graft/bin/gpurun --gpus 8 --timeout 900 -- "$@"
+  /usr/local/graft/bin/gpurun --gpus 8 --timeout 1200 -- "$@"
   rc=$?
   if [ $rc -ne 3 ]; then exit $rc; fi
   sleep 120

@@ -181,6 +181,15 @@ class NvmlClockSampler:
         return out
 
 
+_REAL_STDOUT = None
+
+
+def _emit(line):
+    out = _REAL_STDOUT if _REAL_STDOUT is not None else sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def make_clock_sampler(index):
     try:
         return NvmlClockSampler(index)
@@ -263,7 +272,7 @@ def run_reference(args):
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    _emit(line)
     return 0
 
 
@@ -558,7 +567,7 @@ def run_gpu(args):
                           f"({sum(times):.2f} s wall in total), std::thread x {threads}"}
         except Exception as exc:  # the checker library is test infrastructure; its absence must not hide the GPU number
             line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 0, "kind": "unavailable", "sample": str(exc)}
-    print(json.dumps(line), flush=True)
+    _emit(line)
     if dist is not None:
         dist.destroy_process_group()
     return 0
@@ -605,6 +614,12 @@ def main():
     ap.add_argument("--no-variants", dest="variants", action="store_false", help="skip the offered-variant records (f32 SampleMSC)")
     ap.add_argument("--shower-primaries", type=int, default=4096, help="BASELINE configs[4] record: primaries per GPU (0: skip)")
     args = ap.parse_args()
+    # the contract is ONE JSON line on stdout: whatever a library prints there while the bench runs (NCCL writes its version
+    # line to stdout on the 8-GPU box) goes to stderr instead; the line itself is written to the real stdout at the end
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     if args.impl == "reference":
         return run_reference(args)
     return run_gpu(args)

@@ -142,6 +142,8 @@ struct G4HB200 {
   bool graphTail = true;
   int64_t tailBelow = 1 << 20;
   bool Fused(int64_t n) const { return n < fusedBelow; }
+  // the single-launch e-/e+ step has no single-precision SampleMSC: with that variant on, the pipeline runs
+  bool FusedElectron(int64_t n) const { return n < fusedBelow && !mscF32; }
   // device batches of at least this many tracks run as two half-batch pipelines side by side (G4HB200_SPLIT_MIN)
   int64_t splitThreshold = 1 << 18;
   int splitParts = 2;  // G4HB200_SPLIT_PARTS, at most kNumSlots
@@ -1350,11 +1352,11 @@ int g4hb200_electron_howfar(G4HB200* h, G4HB200ElectronBatch* dev, uint64_t seed
   return LaunchElectronHowFar(h, dev, seed, stream);
 }
 int g4hb200_electron_perform(G4HB200* h, G4HB200ElectronBatch* dev, G4HB200SecondaryQueue* sec, uint64_t seed, void* stream) {
-  if (h != nullptr && dev != nullptr && h->Fused(dev->n)) return LaunchElectronFused<true>(h, dev, sec, seed, stream);
+  if (h != nullptr && dev != nullptr && h->FusedElectron(dev->n)) return LaunchElectronFused<true>(h, dev, sec, seed, stream);
   return LaunchElectronPipelineHalves<false>(h, dev, sec, seed, stream);
 }
 int g4hb200_electron_step(G4HB200* h, G4HB200ElectronBatch* dev, G4HB200SecondaryQueue* sec, uint64_t seed, void* stream) {
-  if (h != nullptr && dev != nullptr && h->Fused(dev->n)) return LaunchElectronFused<false>(h, dev, sec, seed, stream);
+  if (h != nullptr && dev != nullptr && h->FusedElectron(dev->n)) return LaunchElectronFused<false>(h, dev, sec, seed, stream);
   return LaunchElectronPipelineHalves<true>(h, dev, sec, seed, stream);
 }
 int g4hb200_gamma_howfar(G4HB200* h, G4HB200GammaBatch* dev, uint64_t seed, void* stream) {
@@ -1499,7 +1501,7 @@ int g4hb200_electron_step_host(G4HB200* h, G4HB200ElectronBatch* host, G4HB200Se
     q.parent_base = static_cast<int32_t>(lo);
     // H2D: the 7 persistent groups + meta (128 B / track)
     if ((rc = CopyElectron(&hv, &dv, cudaMemcpyHostToDevice, slot.stream, 0, 7, true, false)) != 0) return rc;
-    if ((rc = h->Fused(len) ? LaunchElectronFused<false>(h, &dv, &q, seed, slot.stream, nullptr, c % G4HB200::kNumSlots)
+    if ((rc = h->FusedElectron(len) ? LaunchElectronFused<false>(h, &dv, &q, seed, slot.stream, nullptr, c % G4HB200::kNumSlots)
                        : LaunchElectronPipeline<true>(h, &dv, &q, seed, slot.stream, c % G4HB200::kNumSlots)) != 0)
       return rc;
     // D2H: persistent + result groups + meta + winner (180 B / track)

@@ -352,7 +352,7 @@ int RunStepLoop(G4HB200* h, const G4HB200SlabGeometry* geom, int64_t numPrimarie
         // HowFar + geometry step + Perform: the head of the pipeline does the first two and the along-step part of
         // the third in one pass (ShowerElectronHeadKernel), the queue kernels of Perform follow
         const SlabHead slab{g, s.elGeo[cur]};
-        if ((status = h->Fused(nEl) ? LaunchElectronFused<false>(h, &b, &s.secEl, seed, st, &slab)
+        if ((status = h->FusedElectron(nEl) ? LaunchElectronFused<false>(h, &b, &s.secEl, seed, st, &slab)
                                : LaunchElectronPipelineHalves<true>(h, &b, &s.secEl, seed, st, &slab)) != 0)
           break;
       }

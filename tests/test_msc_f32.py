@@ -73,3 +73,29 @@ def test_msc_f32_variant_within_stated_bound(engine, flat_tables):
     length = np.linalg.norm(p64, axis=1)
     has = same & (length > 0)
     assert (np.linalg.norm(p64 - p32, axis=1)[has] / length[has]).max() <= 2e-4
+
+
+def test_showers_with_f32_msc_keep_the_energy_balance_and_the_sampling_fraction(engine):
+    """The variant inside the stepping loop (512 x 1 GeV showers in the TestEm3 stack): trajectories leave the FP64 ones after
+    a few steps (1e-6 on a direction is a different slab crossing a hundred steps later), so the comparison is physical: kinetic
+    energy in = deposits + leakage exactly as in the FP64 loop (up to 2 m_e c^2 per e+ that leaves), and the share of the
+    deposit taken by the lead within 0.5 % (absolute) of the FP64 run's -- statistics of 512 showers, not precision."""
+    from g4hepem_b200 import shower
+
+    calo = shower.SlabCalorimeter()
+    nprim, ekin = 512, 1000.0
+    res = {}
+    try:
+        for bits in (64, 32):
+            engine.set_msc_precision(bits)
+            res[bits] = shower.run(engine, calo, nprim, ekin, SEED, capacity=1 << 21)
+    finally:
+        engine.set_msc_precision(64)
+    frac = {}
+    for bits, r in res.items():
+        total = r.edep.sum() + r.stats["leak_electron"] + r.stats["leak_gamma"]
+        missing = (nprim * ekin - total) / (2 * 0.51099891)
+        assert missing > -1e-3 and abs(missing - round(missing)) < 1e-3 and round(missing) < 200, (bits, missing)
+        frac[bits] = r.edep[:, 0].sum() / r.edep.sum()
+    assert abs(frac[32] - frac[64]) < 5e-3, frac
+    assert abs(res[32].stats["electron_track_steps"] / res[64].stats["electron_track_steps"] - 1.0) < 2e-2

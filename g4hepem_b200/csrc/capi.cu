@@ -1559,14 +1559,76 @@ int g4hb200_gamma_step_host(G4HB200* h, G4HB200GammaBatch* host, G4HB200Secondar
     if ((rc = g4hb200_secondary_queue_alloc(h, 2 * n, &h->secDev)) != 0) return rc;
     h->secCap = 2 * n;
   }
-  cudaStream_t st = h->stream;
-  if ((rc = CopyGamma(host, &h->gmDev, cudaMemcpyHostToDevice, st, 0, 3, true, false)) != 0) return rc;
-  if ((rc = g4hb200_secondary_queue_reset(h, &h->secDev, st)) != 0) return rc;
-  if ((rc = h->Fused(n) ? LaunchGammaFused<2>(h, &h->gmDev, &h->secDev, seed, st) : LaunchGammaPipeline<2>(h, &h->gmDev, &h->secDev, seed, st)) != 0)
-    return rc;
-  if ((rc = CopyGamma(&h->gmDev, host, cudaMemcpyDeviceToHost, st, 0, 5, true, true)) != 0) return rc;
-  if ((rc = g4hb200_secondary_queue_download(h, &h->secDev, hostSec, st)) != 0) return rc;
-  G4H_CUDA(cudaStreamSynchronize(st));
+  // small batches (and the single-launch option): one upload, one pipeline, one download
+  if (n < 131072 || h->Fused(n)) {
+    cudaStream_t st = h->stream;
+    // the winner index travels too: a photon that ends its step on a boundary keeps the one it came with
+    if ((rc = CopyGamma(host, &h->gmDev, cudaMemcpyHostToDevice, st, 0, 3, true, true)) != 0) return rc;
+    if ((rc = g4hb200_secondary_queue_reset(h, &h->secDev, st)) != 0) return rc;
+    if ((rc = h->Fused(n) ? LaunchGammaFused<2>(h, &h->gmDev, &h->secDev, seed, st) : LaunchGammaPipeline<2>(h, &h->gmDev, &h->secDev, seed, st)) != 0)
+      return rc;
+    if ((rc = CopyGamma(&h->gmDev, host, cudaMemcpyDeviceToHost, st, 0, 5, true, true)) != 0) return rc;
+    if ((rc = g4hb200_secondary_queue_download(h, &h->secDev, hostSec, st)) != 0) return rc;
+    G4H_CUDA(cudaStreamSynchronize(st));
+    return 0;
+  }
+  // large ones in chunks on the two gamma work slots, like g4hb200_electron_step_host: while chunk c computes, chunk c+1
+  // uploads and chunk c-1 downloads (68 B in, 100 B + secondaries out per track)
+  if (h->pinnedCounts == nullptr) {
+    G4H_CUDA(cudaMallocHost(reinterpret_cast<void**>(&h->pinnedCounts), G4HB200::kMaxChunks * sizeof(int32_t)));
+    G4H_CUDA(cudaMalloc(reinterpret_cast<void**>(&h->chunkCounters), G4HB200::kMaxChunks * sizeof(int32_t)));
+  }
+  G4HB200::WorkSlot* gslot[2] = {&h->gmSlot, &h->gmSlot2};
+  for (auto* slot : gslot) {
+    if (slot->stream == nullptr) {
+      G4H_CUDA(cudaStreamCreateWithFlags(&slot->stream, cudaStreamNonBlocking));
+      G4H_CUDA(cudaEventCreateWithFlags(&slot->counted, cudaEventDisableTiming));
+    }
+  }
+  int64_t chunk = ((n / 4 + 32767) / 32768) * 32768;
+  if (chunk < 65536) chunk = 65536;
+  if (chunk > 262144) chunk = 262144;
+  while ((n + chunk - 1) / chunk > G4HB200::kMaxChunks) chunk *= 2;
+  const int numChunks = static_cast<int>((n + chunk - 1) / chunk);
+  G4H_CUDA(cudaMemsetAsync(h->chunkCounters, 0, numChunks * sizeof(int32_t), gslot[0]->stream));
+  G4H_CUDA(cudaStreamSynchronize(gslot[0]->stream));
+  std::vector<cudaEvent_t> counted(numChunks);
+  for (int c = 0; c < numChunks; ++c) {
+    cudaStream_t cs = gslot[c & 1]->stream;
+    const int64_t lo = c * chunk, len = (lo + chunk <= n) ? chunk : n - lo;
+    G4HB200GammaBatch hv = GammaBatchView(*host, lo, len);
+    G4HB200GammaBatch dv = GammaBatchView(h->gmDev, lo, len);
+    G4HB200SecondaryQueue q = h->secDev;
+    q.capacity = 2 * len;
+    q.dirx_diry += 4 * lo;
+    q.dirz_ekin += 4 * lo;
+    q.parent_kind += 4 * lo;
+    q.parent_slot += 4 * lo;
+    q.count = h->chunkCounters + c;
+    q.parent_base = static_cast<int32_t>(lo);
+    if ((rc = CopyGamma(&hv, &dv, cudaMemcpyHostToDevice, cs, 0, 3, true, true)) != 0) return rc;
+    if ((rc = LaunchGammaPipeline<2>(h, &dv, &q, seed, cs, (c & 1) != 0)) != 0) return rc;
+    if ((rc = CopyGamma(&dv, &hv, cudaMemcpyDeviceToHost, cs, 0, 5, true, true)) != 0) return rc;
+    G4H_CUDA(cudaMemcpyAsync(h->pinnedCounts + c, h->chunkCounters + c, sizeof(int32_t), cudaMemcpyDeviceToHost, cs));
+    G4H_CUDA(cudaEventCreateWithFlags(&counted[c], cudaEventDisableTiming));
+    G4H_CUDA(cudaEventRecord(counted[c], cs));
+  }
+  int64_t total = 0;
+  for (int c = 0; c < numChunks; ++c) {
+    cudaStream_t cs = gslot[c & 1]->stream;
+    G4H_CUDA(cudaEventSynchronize(counted[c]));
+    cudaEventDestroy(counted[c]);
+    const int64_t lo = c * chunk;
+    const int64_t cnt = h->pinnedCounts[c];
+    const size_t off2 = static_cast<size_t>(2 * total);
+    G4H_CUDA(cudaMemcpyAsync(hostSec->dirx_diry + off2, h->secDev.dirx_diry + 4 * lo, static_cast<size_t>(cnt) * 16, cudaMemcpyDeviceToHost, cs));
+    G4H_CUDA(cudaMemcpyAsync(hostSec->dirz_ekin + off2, h->secDev.dirz_ekin + 4 * lo, static_cast<size_t>(cnt) * 16, cudaMemcpyDeviceToHost, cs));
+    G4H_CUDA(cudaMemcpyAsync(hostSec->parent_kind + off2, h->secDev.parent_kind + 4 * lo, static_cast<size_t>(cnt) * 8, cudaMemcpyDeviceToHost, cs));
+    G4H_CUDA(cudaMemcpyAsync(hostSec->parent_slot + off2, h->secDev.parent_slot + 4 * lo, static_cast<size_t>(cnt) * 8, cudaMemcpyDeviceToHost, cs));
+    total += cnt;
+  }
+  for (auto* slot : gslot) G4H_CUDA(cudaStreamSynchronize(slot->stream));
+  hostSec->count[0] = static_cast<int32_t>(total);
   return 0;
 }
 

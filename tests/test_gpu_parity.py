@@ -281,6 +281,27 @@ def test_host_buffer_entry_point(engine, reference, flat_tables):
     assert compare.total_bad(compare.compare_secondaries(qwant, qgot)) == 0
 
 
+def test_host_buffer_entry_points_in_chunks(engine, reference, flat_tables):
+    """Batches large enough for the chunked form of the host-buffer calls (upload, pipelines and download of different
+    chunks overlapped on several streams; a ragged last chunk): the same results as the reference, secondaries in one
+    host queue whatever the chunking."""
+    n = 300007
+    host = batches.make_electron_batch(n, flat_tables.num_matcut, seed=141)
+    want = host.copy()
+    qwant = batches.SecondaryHostQueue(2 * n)
+    reference.electron_step(want, qwant, SEED, 8)
+    qgot = batches.SecondaryHostQueue(2 * n)
+    engine.electron_step_host(host, qgot, SEED)
+    _assert_electron(want, host, qwant, qgot, handover=False)
+    g = batches.make_gamma_batch(n, flat_tables.num_matcut, boundary_fraction=0.1, seed=142)
+    gw = g.copy()
+    reference.gamma_step(gw, qwant := batches.SecondaryHostQueue(2 * n), SEED, 8)
+    qgot = batches.SecondaryHostQueue(2 * n)
+    engine.gamma_step_host(g, qgot, SEED)
+    assert compare.total_bad(compare.compare_gamma_batches(gw, g)) == 0
+    assert compare.total_bad(compare.compare_secondaries(qwant, qgot)) == 0
+
+
 def test_secondary_queue_overflow_is_reported(engine, flat_tables):
     n = 20000
     host = batches.make_electron_batch(n, flat_tables.num_matcut, seed=43)

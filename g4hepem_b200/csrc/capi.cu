@@ -82,8 +82,8 @@ void AddElectron(ArenaBuilder& ab, G4HB200ElectronTables& e, int numMatCut, int 
   ab.Add(e.sel_rb_data, e.num_sel_rb);
 }
 
-int GridFor(int64_t n, int smCount, int ctasPerSM) {
-  const int64_t want = (n + kThreadsPerBlock - 1) / kThreadsPerBlock;
+int GridFor(int64_t n, int smCount, int ctasPerSM, int threads = kThreadsPerBlock) {
+  const int64_t want = (n + threads - 1) / threads;
   const int64_t full = static_cast<int64_t>(smCount) * ctasPerSM;
   if (want <= 0) return 1;
   if (want >= full) return static_cast<int>(full);
@@ -191,15 +191,15 @@ namespace {
 // work needs.  Every kernel here is a grid-stride loop, and a CTA costs ~2.5 us of launch + first-load latency
 // whatever it does: with the former 8 CTAs per SM a queue kernel over a thousand tracks took 11 us.
 template <class K>
-int OneWave(G4HB200* h, K kernel, int64_t n) {
+int OneWave(G4HB200* h, K kernel, int64_t n, int threads = kThreadsPerBlock) {
   const void* key = reinterpret_cast<const void*>(kernel);
   auto it = h->residentCtas.find(key);
   if (it == h->residentCtas.end()) {
     int perSM = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, kernel, kThreadsPerBlock, 0) != cudaSuccess || perSM < 1) perSM = 1;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, kernel, threads, 0) != cudaSuccess || perSM < 1) perSM = 1;
     it = h->residentCtas.emplace(key, perSM).first;
   }
-  return GridFor(n, h->smCount, it->second);
+  return GridFor(n, h->smCount, it->second, threads);
 }
 
 // the same for a kernel with dynamic shared memory (the refill samplers, g4h_refill.cuh)
@@ -585,9 +585,9 @@ int LaunchGammaPipeline(G4HB200* h, G4HB200GammaBatch* dev, G4HB200SecondaryQueu
   G4H_CUDA(t.Begin(n));
   G4H_CUDA(t.Before(kSGammaHead));
   if (kMode == 2 && slab != nullptr) {
-    ShowerGammaHeadKernel<<<OneWave(h, ShowerGammaHeadKernel, n), kThreadsPerBlock, 0, st>>>(h->view, *dev, w, seed, slab->g, slab->geo);
+    ShowerGammaHeadKernel<<<OneWave(h, ShowerGammaHeadKernel, n, kGammaThreads), kGammaThreads, 0, st>>>(h->view, *dev, w, seed, slab->g, slab->geo);
   } else {
-    GammaHeadKernel<kMode><<<OneWave(h, GammaHeadKernel<kMode>, n), kThreadsPerBlock, 0, st>>>(h->view, *dev, w, seed);
+    GammaHeadKernel<kMode><<<OneWave(h, GammaHeadKernel<kMode>, n, kGammaThreads), kGammaThreads, 0, st>>>(h->view, *dev, w, seed);
   }
   G4H_CUDA(t.After(kSGammaHead));
   // the three samplers side by side; alone on the caller's stream when per-kernel timing is on
@@ -604,7 +604,7 @@ int LaunchGammaPipeline(G4HB200* h, G4HB200GammaBatch* dev, G4HB200SecondaryQueu
     constexpr size_t smem = RefillSmemBytes<GammaRefillSampler<P>::type>();                                                           \
     GammaRefillKernel<P><<<OneWaveSmem(h, GammaRefillKernel<P>, n, smem), kThreadsPerBlock, smem, on>>>(h->view, *dev, w, *sec, seed, rc4); \
   } else {                                                                                                                            \
-    GammaInteractKernel<P><<<OneWave(h, GammaInteractKernel<P>, n), kThreadsPerBlock, 0, on>>>(h->view, *dev, w, *sec, seed);          \
+    GammaInteractKernel<P><<<OneWave(h, GammaInteractKernel<P>, n, kGammaThreads), kGammaThreads, 0, on>>>(h->view, *dev, w, *sec, seed); \
   }                                                                                                                                   \
   G4H_CUDA(t.After(stage, on));
   G4H_GM_SAMPLER(kSGammaCompton, st, kGQCompton)

@@ -15,6 +15,9 @@
 namespace g4h {
 
 constexpr int kThreadsPerBlock = 256;
+// the gamma step's kernels run as 128-thread CTAs, six per SM: measured 3 % faster than 256 x 3 for the 1M-photon step (the
+// e-/e+ kernels are indifferent: 2.00e9 either way; profiles/r02b_schedule_ab.log)
+constexpr int kGammaThreads = 128;
 // resident CTAs per SM the queue kernels are compiled for (register cap = 65536 / (256 * k)); tuned on the B200,
 // see profiles/
 #ifndef G4H_MINB_QUEUE

@@ -217,7 +217,7 @@ ElSamplerKernel(const __grid_constant__ TablesView tv, const __grid_constant__ G
 enum GmQueue { kGQConversion = 0, kGQCompton, kGQPhotoelectric, kNumGmQueues };
 
 template <int kMode>
-__global__ void __launch_bounds__(kThreadsPerBlock, G4H_MINB_QUEUE)
+__global__ void __launch_bounds__(kGammaThreads, 2 * G4H_MINB_QUEUE)
 GammaHeadKernel(const __grid_constant__ TablesView tv, const __grid_constant__ G4HB200GammaBatch b,
                 const __grid_constant__ ElectronWork w, uint64_t seed) {
   const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
@@ -231,7 +231,7 @@ GammaHeadKernel(const __grid_constant__ TablesView tv, const __grid_constant__ G
 }
 
 template <int kProc>
-__global__ void __launch_bounds__(kThreadsPerBlock, G4H_MINB_QUEUE)
+__global__ void __launch_bounds__(kGammaThreads, 2 * G4H_MINB_QUEUE)
 GammaInteractKernel(const __grid_constant__ TablesView tv, const __grid_constant__ G4HB200GammaBatch b,
                     const __grid_constant__ ElectronWork w, const __grid_constant__ G4HB200SecondaryQueue sq, uint64_t seed) {
   const int cnt = w.count[kProc];
@@ -241,7 +241,7 @@ GammaInteractKernel(const __grid_constant__ TablesView tv, const __grid_constant
   // draws per track (tools, reference run): conversion 11-12 (p90), Compton 4-7, photoelectric 1 (median; most
   // photons are absorbed below the K edge without an electron) .. 9 (p90)
   constexpr uint32_t kSlots = kProc == kGQCompton ? G4H_WINDOW_SAMPLER : (kProc == kGQConversion ? 2 * G4H_WINDOW_SAMPLER : 4);
-  __shared__ double window[kSlots * kThreadsPerBlock];
+  __shared__ double window[kSlots * kGammaThreads];
   cc.Init();
   for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < nRound; q += stride) {
     Secondaries sec;
@@ -250,7 +250,7 @@ GammaInteractKernel(const __grid_constant__ TablesView tv, const __grid_constant
     int id = 0;
     if (q < cnt) {
       i = w.queue[kProc][q];
-      StageGammaInteract<kProc>(tv, b, i, seed, sec, id, window + threadIdx.x, kThreadsPerBlock, kSlots);
+      StageGammaInteract<kProc>(tv, b, i, seed, sec, id, window + threadIdx.x, kGammaThreads, kSlots);
     }
     AppendSecondaries(cc, sq, sec, id, i);
   }

@@ -292,7 +292,7 @@ struct SlabGammaGeometryStep {
 
 #if defined(__CUDACC__)
 // ---- the head of a gamma step of the loop: HowFar + geometry step + SelectInteraction + head of Perform -------------
-__global__ void __launch_bounds__(kThreadsPerBlock, G4H_MINB_QUEUE)
+__global__ void __launch_bounds__(kGammaThreads, 2 * G4H_MINB_QUEUE)
 ShowerGammaHeadKernel(const __grid_constant__ TablesView tv, const __grid_constant__ G4HB200GammaBatch b,
                       const __grid_constant__ ElectronWork w, uint64_t seed, const __grid_constant__ SlabGeom g,
                       const __grid_constant__ TrackGeo geo) {

@@ -324,6 +324,29 @@ G4H_LEAF double SplineLog4(const double* data, double x, double logx, double log
                 G4H_LD(data + idx9_0 + iwhich + 1), G4H_LD(data + idx9_1 + iwhich + 1), x);
 }
 
+// The conversion, Compton and photoelectric columns (iwhich = 2, 3, 4) of one row pair in one go: SampleInteraction asks for
+// them one after the other (.icc:196-208) and every call repeats the bin index, the abscissas and the interpolation weight.
+// Same operations per column as Spline() above, hence the same bits.
+G4H_FN void SplineLog4Three(const double* data, double x, double logx, double logxmin, double invLDBin, double* out) {
+  const int idx    = LogBin(logx, logxmin, invLDBin, 256);
+  const double* r0 = data + 9 * idx;
+  const double* r1 = r0 + 9;
+  const double x1 = G4H_LD(r0), x2 = G4H_LD(r1);
+  const double dl = x2 - x1;
+  const double b  = Max(0., Min(1., FastDiv(x - x1, dl)));
+  const double os = 0.166666666667;
+  const double bb = b * (b - 1.0);
+  const double d2 = dl * dl * os;
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    const double y1 = G4H_LD(r0 + 3 + 2 * k), sd1 = G4H_LD(r0 + 4 + 2 * k);
+    const double y2 = G4H_LD(r1 + 3 + 2 * k), sd2 = G4H_LD(r1 + 4 + 2 * k);
+    const double c0 = (2.0 - b) * sd1;
+    const double c1 = (1.0 + b) * sd2;
+    out[k] = y1 + b * (y2 - y1) + bb * (c0 + c1) * d2;
+  }
+}
+
 // GetTotalMacXSec (.icc:108-152); peMXsec is G4HepEmGammaTrack::fPEmxSec (only written in windows 0/1)
 G4H_FN double GammaTotalMacXSec(const TablesView& tv, int imat, double ekin, double lekin, double& peMXsec) {
   const double* matData = tv.gmMXsec + imat * tv.gmDataPerMat;
@@ -368,13 +391,15 @@ G4H_FN int GammaSampleInteraction(const TablesView& tv, int imat, double ekin, d
     // reads one slot past the PE column (out of bounds for the last bin of the last material) and the
     // value cannot change the outcome (winner = 3).  Only the three real columns are evaluated here;
     // fPEmxSec is "garbage otherwise" in the reference (.icc:182) and is set to 0 in that case.
+    double mxSec[3];
+    SplineLog4Three(data, ekin, lekin, tv.gmLogEMin2, tv.gmEILDelta2, mxSec);
     double cProb = 0.0;
-    for (int pid = 2; pid < 5; ++pid) {
-      const double mxSec = SplineLog4(data, ekin, lekin, tv.gmLogEMin2, tv.gmEILDelta2, pid);
-      cProb += mxSec * totMFP;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      cProb += mxSec[k] * totMFP;
       if (!(urnd > cProb)) {
-        peMXsec = mxSec;
-        return pid - 2;
+        peMXsec = mxSec[k];
+        return k;
       }
     }
     peMXsec = 0.0;

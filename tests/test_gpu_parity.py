@@ -454,9 +454,9 @@ def test_electron_fused_step_with_odd_draw_counters(engine, reference, flat_tabl
 
 
 def test_fused_launch_and_stage_pipeline_agree(engine, flat_tables):
-    """The step as one persistent launch with CTA-local queues (g4h_fused.cuh, the default) and as the pipeline of stage
-    kernels over global queues (G4HB200_FUSED=0) run the same stage functions on the same per-track uniform streams in
-    a different order of tracks: state, results and secondaries must agree bit for bit (e-/e+ step, e-/e+ Perform after
+    """The step as one persistent launch with CTA-local queues (g4h_fused.cuh, opt-in: G4HB200_FUSED=1) and as the pipeline
+    of stage kernels over global queues (the default) run the same stage functions on the same per-track uniform streams
+    in a different order of tracks: state, results and secondaries must agree bit for bit (e-/e+ step, e-/e+ Perform after
     HowFar, gamma step), also for a batch that is not a multiple of the CTA size."""
     import os
 
@@ -464,11 +464,23 @@ def test_fused_launch_and_stage_pipeline_agree(engine, flat_tables):
 
     from g4hepem_b200 import engine as eng
 
-    os.environ["G4HB200_FUSED"] = "0"
+    os.environ["G4HB200_FUSED"] = "1"
     try:
-        staged = eng.Engine(flat_tables, device=0)
+        staged = eng.Engine(flat_tables, device=0)  # the other implementation: here the single launch
     finally:
         del os.environ["G4HB200_FUSED"]
+    n0 = 1000
+    host0 = batches.make_electron_batch(n0, flat_tables.num_matcut, seed=90)
+    d0, s0 = eng.ElectronDeviceBatch(n0), eng.SecondaryDeviceQueue(2 * n0)
+    counts = []
+    for e in (engine, staged):
+        d0.upload(host0)
+        s0.reset()
+        before = e.launch_count
+        eng.ElectronManager.Step(e, d0, s0, SEED)
+        torch.cuda.synchronize()
+        counts.append(e.launch_count - before)
+    assert counts[1] < counts[0], counts  # one launch against the pipeline's dozen: the two engines do differ
     for n in (300007, 1000):
         host = batches.make_electron_batch(n, flat_tables.num_matcut, seed=91)
         ghost = batches.make_gamma_batch(n, flat_tables.num_matcut, boundary_fraction=0.1, seed=92)

@@ -12,11 +12,16 @@
 // A trial is ONE pass of the rejection loop for 32 pending entries, whichever pass it is for each of them; the
 // rejected go back to the ring, the accepted move on.  Entries that need no sampling at all never enter a ring.
 // The uniforms of a pass are generated inside the pass by every lane (one or two Philox blocks), so no uniform is
-// generated that is not consumed.  What travels through shared memory per entry: the sampler's Pars (8-11 doubles),
+// generated that is not consumed.  What travels through shared memory per entry: the sampler's Pars (7-11 doubles),
 // track index, track id, draw counter and the unused half of the last Philox block.
 //
 // Results do not depend on any of this: a track's uniforms are a function of (seed, track id, draw index), and its
 // passes see them in the order of the reference's loop.
+//
+// Measured (profiles/r02b_refill_ab.log, r02b_variants_full.md): lanes go up (Bhabha 12.7 -> 24.6, Moller 17.9 -> 26.3) and
+// every kernel but the photoelectric one gets SLOWER -- these kernels are bound by the latency of one warp's instruction
+// stream, a pass through the rings costs more than the lanes it fills, and Setup + Finish outweigh the loop.  The executor
+// is therefore opt-in (G4HB200_REFILL=k); the default runs RunSampler one thread per track (g4h_pipeline.cuh).
 #ifndef G4H_REFILL_CUH
 #define G4H_REFILL_CUH
 
